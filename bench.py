@@ -1,0 +1,298 @@
+"""bench.py -- dates x stocks / second per ELBO step (forward + backward [+ gradient all-reduce]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (FactorVAE.forward + backward, reference module.py:250-270 +
+train_model.py:29) over one batch of synthetic dates.  Workload at N=1: BASELINE.json configs[1]
+(B=256 dates x N=300 stocks x T=20 x C=158, K=H=20, M=128).  For N>1 the per-GPU work is fixed
+(weak scaling): every rank processes B dates of the same shape, dates keyed by their global id.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job units/s with the panel resident in HBM;
+`e2e` = the same through the host-buffer entry (H2D of the batch + D2H of the loss inside the
+timed region); `roofline` / `cpu_baseline` as specified in the task statement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B dates per GPU, N stocks, T, K=H, M)
+    "cfg1": dict(B=1, N=64, T=20, H=20, K=20, M=128),
+    "cfg2": dict(B=256, N=300, T=20, H=20, K=20, M=128),
+    "cfg3": dict(B=256, N=500, T=60, H=60, K=60, M=128),
+    "cfg4": dict(B=64, N=1000, T=20, H=48, K=48, M=128),     # per-GPU share of B=512 over 8 GPUs
+    "cfg5": dict(B=128, N=3000, T=60, H=60, K=60, M=128),    # per-GPU share of B=1024 over 8 GPUs
+}
+C_FEATURES = 158
+METRIC = "dates x stocks / sec per ELBO step (fwd+bwd), K=20 C=158"
+
+
+def f_fe(T, H, C=C_FEATURES):
+    """Algorithmic FLOPs per date x stock per step: FeatureExtractor contractions, fwd + 2x bwd."""
+    return 3 * 2 * T * (C * C + 3 * H * C + 3 * H * H)
+
+
+def build_params(H, K, M, seed=42):
+    import torch
+    import factorvae_b200 as fb
+    torch.manual_seed(seed)
+    model = fb.FactorVAE(fb.FeatureExtractor(C_FEATURES, H), fb.FactorEncoder(K, M, H),
+                         fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, K)), fb.FactorPredictor(H, K))
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self._stop = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def run_reference(args, wl, rank, world):
+    """Reference arm: the reference's CPU implementation of the path (oracle/cpu_port.py -- the Python
+    reference cannot travel to the GPU box) on the host cores, one date per step as train_model.py does."""
+    if rank != 0:
+        return
+    import torch
+    from oracle.cpu_port import CpuPort
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = build_params(wl["H"], wl["K"], wl["M"])
+    port = CpuPort(params)
+    g = torch.Generator().manual_seed(1234)
+    # bounded sample: each step = `dates_per_step` per-date reference steps of the workload's (N, T, K)
+    dates_per_step = 4
+    xs = [torch.randn(wl["N"], wl["T"], C_FEATURES, generator=g).clamp_(-3, 3) for _ in range(dates_per_step)]
+    ys = [torch.randn(wl["N"], 1, generator=g) for _ in range(dates_per_step)]
+    for _ in range(args.warmup):
+        for x, y in zip(xs, ys):
+            port.train_step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for x, y in zip(xs, ys):
+            port.train_step(x, y)
+    dt = time.perf_counter() - t0
+    units = args.steps * dates_per_step * wl["N"]
+    value = units / dt
+    sample = (f"{dates_per_step} dates/step of the workload's per-date shape (N={wl['N']},T={wl['T']},K=H={wl['K']}), one date per "
+              f"reference step (zero_grad, forward, loss.item(), backward; no optimizer), fp32 torch CPU, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "date*stocks/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload_desc},
+            "cpu_baseline": {"value": value, "unit": "date*stocks/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "date*stocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--panel", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.workload_desc = (f"{args.workload}: B={wl['B']} dates/GPU x N={wl['N']} stocks x T={wl['T']} x C={C_FEATURES}, "
+                          f"K=H={wl['K']}, M={wl['M']}; {world} GPU(s), dates sharded, weak scaling")
+    if args.impl == "reference":
+        return run_reference(args, wl, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from factorvae_b200 import _cabi, engine
+    from factorvae_b200.batched import DateShardedStep
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, T, H, K, M = (wl[k] for k in "BNTHKM")
+    S = B * N
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if engine.tc_supported(C_FEATURES, H) else "fp32"
+    params = build_params(H, K, M)
+    layout = engine.ParamLayout(C_FEATURES, H, K, M)
+    flat = layout.pack(params, dev)
+
+    # synthetic panel: N(0,1) clipped to +-3 per GLOBAL date id (identical global batch for any sharding)
+    pdt = torch.bfloat16 if args.panel == "bf16" else torch.float32
+    x = torch.empty(S, T, C_FEATURES, dtype=pdt, device=dev)
+    y = torch.empty(S, dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev)
+    for d in range(B):
+        gen.manual_seed(1234 + rank * B + d)
+        x[d * N:(d + 1) * N] = torch.randn(N, T, C_FEATURES, generator=gen, device=dev).clamp_(-3, 3).to(pdt)
+        y[d * N:(d + 1) * N] = torch.randn(N, generator=gen, device=dev)
+    date_ptr = engine.uniform_date_ptr(B, N, dev)
+    stepper = DateShardedStep(layout, flat, precision=precision, seed=42)
+    unit_base = rank * S
+    lib = _cabi.lib()
+
+    def one_step():
+        stepper.step(x, y, date_ptr, global_dates=B * world, unit_base=unit_base, train=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = lib.fvae_debug_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    ev1.record()
+    barrier()
+    launches = lib.fvae_debug_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = ev0.elapsed_time(ev1)
+    loss_val = float(stepper.loss.item())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * S / (ms_per_step * 1e-3)
+
+    # ---- phase timing on the launching stream (FeatureExtractor chain alone), for the roofline
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    flops_step = S * f_fe(T, H)
+    achieved_tf = flops_step / (ms_per_step * 1e-3) / 1e12
+    fe_ms = None
+    if rank == 0:
+        e, saved = engine.fe_forward(layout, flat, x, precision)
+        de = torch.randn_like(e)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, args.steps // 4)
+        a0.record()
+        for _ in range(reps):
+            e, saved = engine.fe_forward(layout, flat, x, precision)
+            engine.fe_backward(layout, saved, de)
+        a1.record()
+        torch.cuda.synchronize()
+        fe_ms = a0.elapsed_time(a1) / reps
+        del e, saved, de
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": None, "peak_source": peak_src,
+                "note": "whole ELBO step (all kernels) against the dense bf16 tensor peak; algorithmic FLOPs = "
+                        "S*3*2T(C^2+3HC+3H^2) (FeatureExtractor contractions, unpadded)",
+                "fe_chain_ms": fe_ms,
+                "fe_chain_frac": (flops_step / (fe_ms * 1e-3) / 1e12 / peak_tf) if fe_ms else None,
+                "hbm_algorithmic_gbs": S * (T * C_FEATURES * (2 if args.panel == "bf16" else 4) + 4) / (ms_per_step * 1e-3) / 1e9}
+
+    # ---- end to end through the host-buffer entry (pinned fp32 host panel as the reference's loader yields)
+    e2e = None
+    if not args.no_e2e:
+        xh = x.float().to("cpu").pin_memory()      # fp32 host panel, as the reference loader yields (train_model.py:23)
+        yh = y.to("cpu").pin_memory()
+        ph = date_ptr.to("cpu").pin_memory()
+        for _ in range(3):
+            stepper.step_from_host(xh, yh, ph, global_dates=B * world, unit_base=unit_base, train=True)
+        barrier()
+        n_e2e = max(3, args.steps // 2)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(n_e2e):
+            stepper.step_from_host(xh, yh, ph, global_dates=B * world, unit_base=unit_base, train=True)
+        b1.record()
+        barrier()
+        t2 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item()) / n_e2e
+        e2e = {"value": world * S / (e2e_ms * 1e-3), "unit": "date*stocks/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": xh.numel() * xh.element_size() + yh.numel() * 4 + ph.numel() * 4,
+               "d2h_bytes_per_step": 4, "host_panel_dtype": str(xh.dtype).replace("torch.", "")}
+        del xh, yh
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.cpu_port import time_cpu_steps
+        v, ms_date, nsteps, cores = time_cpu_steps(params, N, T, C_FEATURES, budget_s=10.0)
+        cpu_baseline = {"value": v, "unit": "date*stocks/s", "cores": cores, "kind": "port",
+                        "sample": f"{nsteps} per-date reference-style steps (N={N},T={T},K=H={K}; zero_grad, forward, "
+                                  f"loss.item(), backward) in ~10 s, median {ms_date:.2f} ms/date, fp32 torch CPU"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "date*stocks/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": args.workload_desc, "panel_dtype": args.panel, "precision": precision,
+                           "l2": "inputs larger than L2 (panel %.0f MB per GPU)" % (x.numel() * x.element_size() / 1e6),
+                           "noise": "in-kernel Philox (eps + dropout masks), keyed by global unit id",
+                           "parallelism": f"dp{world} over dates"},
+                "loss": loss_val, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "e2e": e2e}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+"""Date-batched, date-sharded ELBO step -- the extension that sits next to the reference's per-date
+loop (train_model.py:17-30; the reference has no date batch and no data parallelism).
+
+Semantics: for a global batch of B dates,
+    L = (1/B) sum_d [ mean_i (yhat_di - y_di)^2 + KL_d ],
+i.e. B=1 is the reference step and grad L is the mean of B reference per-date gradients.
+
+Multi-GPU: dates are independent (every cross-sectional op is within one date), so each rank takes a
+contiguous block of dates, runs the same kernel chain on its block and the ranks exchange exactly ONE
+buffer per step: the flat fp32 gradient with the loss riding in its tail (<= 2.2 MB, latency bound on
+NVLink/NVSwitch).  Noise is keyed by the GLOBAL unit index, so results do not depend on the sharding.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import engine
+
+
+def shard_dates(B: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [d0, d1) of the B global dates owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(B, world)
+    d0 = rank * base + min(rank, rem)
+    return d0, d0 + base + (1 if rank < rem else 0)
+
+
+class DateShardedStep:
+    def __init__(self, layout: engine.ParamLayout, flat: torch.Tensor, precision: str = "bf16", group=None,
+                 seed: int = 42):
+        self.layout, self.flat, self.precision, self.group, self.seed = layout, flat, precision, group, seed
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # gradient buffer with a 4-float tail: [total] = loss (written by the kernels), rest padding
+        self.gradbuf = torch.zeros(layout.total + 4, dtype=torch.float32, device=flat.device)
+        self.workspace: Optional[torch.Tensor] = None
+        self.step_index = 0
+        self._dev: Dict[str, torch.Tensor] = {}
+
+    @property
+    def grad(self) -> torch.Tensor:
+        return self.gradbuf[: self.layout.total]
+
+    @property
+    def loss(self) -> torch.Tensor:
+        return self.gradbuf[self.layout.total: self.layout.total + 1]
+
+    def step(self, x: torch.Tensor, y: torch.Tensor, date_ptr: torch.Tensor, *, global_dates: Optional[int] = None,
+             unit_base: int = 0, train: bool = True, eps: Optional[torch.Tensor] = None,
+             keep_mask: Optional[torch.Tensor] = None):
+        """Forward + backward over this rank's dates, then the single gradient all-reduce.
+
+        x (S_local, T, C), y (S_local,), date_ptr (B_local+1,) local CSR.  global_dates = B of the whole
+        batch (default: B_local * world).  Returns (outputs, state); self.grad / self.loss hold the
+        GLOBAL-batch gradient / loss afterwards."""
+        self.step_index += 1
+        B_local = date_ptr.numel() - 1
+        B_global = global_dates if global_dates is not None else B_local * self.world
+        noise = dict(eps=eps, keep_mask=keep_mask) if eps is not None else dict(philox=(self.seed, self.step_index, unit_base))
+        out, st = engine.elbo_forward(self.layout, self.flat, x, y, date_ptr, train=train, precision=self.precision,
+                                      workspace=self.workspace, loss_out=self.loss, **noise)
+        self.workspace = st.workspace
+        engine.elbo_backward(self.layout, st, grad=self.grad)
+        if self.world > 1:
+            if B_local * self.world == B_global and dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.gradbuf, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                self.gradbuf.mul_(float(B_local) / float(B_global))
+                dist.all_reduce(self.gradbuf, op=dist.ReduceOp.SUM, group=self.group)
+        elif B_local != B_global:
+            self.gradbuf.mul_(float(B_local) / float(B_global))
+        return out, st
+
+    def step_from_host(self, x_host: torch.Tensor, y_host: torch.Tensor, date_ptr_host: torch.Tensor, **kw):
+        """End-to-end entry: pinned HOST buffers in, loss (a Python float) out -- the H2D copy of the
+        batch and the D2H read of the loss are part of the call."""
+        dev = self.flat.device
+        for name, src in (("x", x_host), ("y", y_host), ("date_ptr", date_ptr_host)):
+            buf = self._dev.get(name)
+            if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+                buf = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                self._dev[name] = buf
+            buf.copy_(src, non_blocking=True)
+        out, st = self.step(self._dev["x"], self._dev["y"], self._dev["date_ptr"], **kw)
+        return float(self.loss.item()), out, st
+
+    def assign_grads(self, model) -> None:
+        """Expose the flat gradient as `.grad` of the model's parameters (views, no copy)."""
+        for name, p in model.named_parameters():
+            p.grad = self.layout.view(self.grad, name)

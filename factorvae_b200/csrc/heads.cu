@@ -1,0 +1,831 @@
+// Cross-sectional heads of the FactorVAE ELBO step, fp32 CUDA-core kernels (sm_100a).
+//
+// One CTA per DATE.  Everything that couples the stocks of a date lives here:
+//   FactorEncoder   (reference module.py:52-67, :44-50)  softmax over STOCKS, portfolio returns
+//   FactorPredictor (module.py:169-188, AttentionLayer :134-153) -- the K heads are collapsed:
+//         score_ik = (e_i . G_k + c_k)/sqrt(H+1e-6),  G_k = Wk_k^T q_k,  c_k = q_k . bk_k
+//         ctx_k    = Wv_k (sum_i a_ik e_i) + bv_k
+//   FactorDecoder   (module.py:107-123) alpha/beta heads, mu_y / sigma_y, reparameterisation
+//   loss            (module.py:261-268) mean-squared error of the sample + KL(post || prior)
+//
+// Work decomposition inside a CTA: "thread per weight row".  All per-stock contractions have the
+// form F[i][c] = e_i . w_c with w_c a length-H weight row (rows of Wp, G, Wb, Wa).  A thread owns
+// one row c, keeps it in registers and sweeps the stocks of the date in chunks of 64 staged in
+// shared memory (all lanes read the same e_i -> broadcast LDS.128).  Column softmaxes over stocks
+// are online (running max / sum), so one sweep gives the encoder and attention statistics.
+// Backward uses the same ownership for the weight gradients (dW_c = sum_i Z[i][c] e_i held in
+// registers, flushed once per CTA with red.global.add) and a second mapping (thread per stock x
+// quarter of H) for dE = Z . Wcat.
+//
+// HBM traffic: e (S x H fp32) is read twice forward / three times backward, from L2 in practice.
+#include <float.h>
+
+#include "heads.cuh"
+
+namespace fvae {
+
+namespace {
+
+constexpr int CH = 64;    // stocks per shared-memory chunk
+constexpr int NT = 256;   // threads per CTA
+
+__device__ __forceinline__ bool is_finite(float v) { return fabsf(v) <= FLT_MAX; }
+
+template <int HP>
+__device__ __forceinline__ float dot_row(const float (&w)[HP], const float* __restrict__ erow) {
+    const float4* e4 = reinterpret_cast<const float4*>(erow);
+    float acc = 0.f;
+#pragma unroll
+    for (int h4 = 0; h4 < HP / 4; ++h4) {
+        float4 v = e4[h4];
+        acc = fmaf(w[4 * h4 + 0], v.x, acc);
+        acc = fmaf(w[4 * h4 + 1], v.y, acc);
+        acc = fmaf(w[4 * h4 + 2], v.z, acc);
+        acc = fmaf(w[4 * h4 + 3], v.w, acc);
+    }
+    return acc;
+}
+
+template <int HP>
+__device__ __forceinline__ void load_row(float (&w)[HP], const float* __restrict__ src, int H, bool active) {
+#pragma unroll
+    for (int h = 0; h < HP; ++h) w[h] = (active && h < H) ? src[h] : 0.f;
+}
+
+__device__ __forceinline__ float keep_factor(const HeadsArgs& a, int unit, int k) {
+    // dropout on the attention scores (module.py:144): kept -> 1/0.9, dropped -> 0; eval -> 1
+    if (!(a.flags & FVAE_FLAG_TRAIN)) return 1.f;
+    bool keep;
+    if (a.noise.keep_mask) keep = a.noise.keep_mask[size_t(unit) * a.K + k] != 0;
+    else keep = philox_keep(a.noise.seed, a.noise.step, a.noise.unit_base + unit, k);
+    return keep ? kKeepScale : 0.f;
+}
+
+__device__ __forceinline__ float eps_of(const HeadsArgs& a, int unit) {
+    if (a.noise.eps) return a.noise.eps[unit];
+    return philox_normal(a.noise.seed, a.noise.step, a.noise.unit_base + unit);
+}
+
+// relu that propagates NaN like torch (fmaxf would swallow it)
+__device__ __forceinline__ float relu_nan(float s) { return (s > 0.f || s != s) ? s : 0.f; }
+
+struct Smem {
+    float *Es, *ys, *aux0, *aux1, *red, *yp, *muz, *sgz, *mupr, *sgpr, *pooled, *ctx, *F;
+    int* bad;
+    int FLD;
+};
+
+// ------------------------------------------------------------------------------------------
+// prep: collapse the K attention heads' key projections (date independent)
+// ------------------------------------------------------------------------------------------
+__global__ void heads_prep_kernel(HeadsArgs a, int zero_acc) {
+    const int k = blockIdx.x, H = a.H;
+    const float* q = a.w.q + size_t(k) * H;
+    const float* Wk = a.w.Wk + size_t(k) * H * H;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float g = 0.f;
+        for (int hp = 0; hp < H; ++hp) g = fmaf(q[hp], Wk[hp * H + h], g);
+        a.sv.G[k * H + h] = g;
+        if (zero_acc) a.sv.dG[k * H + h] = 0.f;
+    }
+    if (threadIdx.x == 0) {
+        float c = 0.f;
+        for (int h = 0; h < H; ++h) c = fmaf(q[h], a.w.bk[size_t(k) * H + h], c);
+        a.sv.cvec[k] = c;
+        if (zero_acc) a.sv.dc[k] = 0.f;
+    }
+}
+
+// backward of prep: dq, dWk, dbk from the accumulated dG, dc
+__global__ void heads_post_kernel(HeadsArgs a, HeadsG g) {
+    const int k = blockIdx.x, H = a.H;
+    const float* q = a.w.q + size_t(k) * H;
+    const float* Wk = a.w.Wk + size_t(k) * H * H;
+    const float* bk = a.w.bk + size_t(k) * H;
+    const float* dG = a.sv.dG + size_t(k) * H;
+    const float dc = a.sv.dc[k];
+    // a head that tripped the guard on every date has dG == dc == 0 exactly and must get exact
+    // zeros even if q / Wk hold inf (0*inf): branch instead of multiplying.
+    for (int idx = threadIdx.x; idx < H * H; idx += blockDim.x) {
+        int hp = idx / H, h = idx % H;
+        float d = dG[h];
+        g.Wk[size_t(k) * H * H + idx] = (d == 0.f) ? 0.f : q[hp] * d;
+    }
+    for (int hp = threadIdx.x; hp < H; hp += blockDim.x) {
+        float acc = 0.f;
+        for (int h = 0; h < H; ++h) { float d = dG[h]; if (d != 0.f) acc = fmaf(Wk[hp * H + h], d, acc); }
+        if (dc != 0.f) acc = fmaf(bk[hp], dc, acc);
+        g.q[size_t(k) * H + hp] = acc;
+        g.bk[size_t(k) * H + hp] = (dc == 0.f) ? 0.f : q[hp] * dc;
+    }
+}
+
+__global__ void loss_reduce_kernel(const float* __restrict__ date_loss, int B, float* __restrict__ loss) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int d = threadIdx.x; d < B; d += blockDim.x) acc += date_loss[d];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) *loss = acc / float(B);
+}
+
+__device__ __forceinline__ Smem carve(float* smem, int HP, int H, int K, int M, int fld) {
+    Smem s;
+    s.Es = smem;                 smem += CH * HP;
+    s.ys = smem;                 smem += CH;
+    s.aux0 = smem;               smem += CH;
+    s.aux1 = smem;               smem += CH;
+    s.red = smem;                smem += 32;
+    s.yp = smem;                 smem += M;
+    s.muz = smem;                smem += K;
+    s.sgz = smem;                smem += K;
+    s.mupr = smem;               smem += K;
+    s.sgpr = smem;               smem += K;
+    s.bad = reinterpret_cast<int*>(smem); smem += K;
+    s.pooled = smem;             smem += K * H;
+    s.ctx = smem;                smem += K * H;
+    s.F = smem;
+    s.FLD = fld;
+    return s;
+}
+
+template <int HP>
+__device__ __forceinline__ void stage_chunk(const HeadsArgs& a, const Smem& s, int p0, int i0, int cn) {
+    const int H = a.H;
+    for (int idx = threadIdx.x; idx < CH * HP; idx += NT) {
+        int i = idx / HP, h = idx % HP;
+        s.Es[idx] = (i < cn && h < H) ? a.e[size_t(p0 + i0 + i) * H + h] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int HP>
+__global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const int H = a.H, K = a.K, M = a.M;
+    const int d = blockIdx.x, tid = threadIdx.x;
+    const int p0 = a.date_ptr[d], n = a.date_ptr[d + 1] - p0;
+    const int FLD = (K + H) | 1;
+    Smem s = carve(smem_raw, HP, H, K, M, FLD);
+    if (n <= 0) { if (tid == 0 && a.out.date_loss) a.out.date_loss[d] = nanf(""); return; }
+    const float tau = sqrtf(float(H) + 1e-6f);          // module.py:142, evaluated in fp32
+
+    // ---- pass A: online column softmax over the stocks for encoder (M) and attention (K) columns
+    const int colA0 = a.predict ? M : 0;
+    const int ncolA = a.predict ? K : M + K;
+    for (int cb = 0; cb < ncolA; cb += NT) {
+        const int c = colA0 + cb + tid;
+        const bool act = (cb + tid) < ncolA;
+        const bool is_att = c >= M;
+        const int k = c - M;
+        float w[HP];
+        load_row<HP>(w, is_att ? a.sv.G + size_t(act ? k : 0) * H : a.w.Wp + size_t(act ? c : 0) * H, H, act);
+        const float bias = !act ? 0.f : (is_att ? a.sv.cvec[k] : a.w.bp[c]);
+        float m = -INFINITY, l = 0.f, accy = 0.f;
+        float accp[HP];
+#pragma unroll
+        for (int h = 0; h < HP; ++h) accp[h] = 0.f;
+        int bad = 0;
+        for (int i0 = 0; i0 < n; i0 += CH) {
+            const int cn = min(CH, n - i0);
+            __syncthreads();
+            stage_chunk<HP>(a, s, p0, i0, cn);
+            if (tid < CH) s.ys[tid] = (!a.predict && tid < cn) ? a.y[p0 + i0 + tid] : 0.f;
+            __syncthreads();
+            if (!act) continue;
+            for (int i = 0; i < cn; ++i) {
+                const float* er = s.Es + i * HP;
+                float x = dot_row<HP>(w, er) + bias;
+                if (is_att) {
+                    x = x / tau;
+                    x = x * keep_factor(a, p0 + i0 + i, k);
+                    x = relu_nan(x);
+                    if (!is_finite(x)) bad = 1;
+                }
+                float p;
+                if (x > m) {                      // new running maximum: rescale what we have
+                    const float sc = expf(m - x);
+                    l *= sc; accy *= sc;
+                    if (is_att) {
+#pragma unroll
+                        for (int h = 0; h < HP; ++h) accp[h] *= sc;
+                    }
+                    m = x; p = 1.f;
+                } else {
+                    p = expf(x - m);
+                }
+                l += p;
+                if (is_att) {
+#pragma unroll
+                    for (int h = 0; h < HP; ++h) accp[h] = fmaf(p, er[h], accp[h]);
+                } else {
+                    accy = fmaf(p, s.ys[i], accy);
+                }
+            }
+        }
+        if (act) {
+            if (is_att) {
+                a.sv.att_m[size_t(d) * K + k] = m;
+                a.sv.att_l[size_t(d) * K + k] = l;
+                a.sv.bad[size_t(d) * K + k] = bad;
+                s.bad[k] = bad;
+                const float inv = 1.f / l;
+#pragma unroll
+                for (int h = 0; h < HP; ++h)
+                    if (h < H) {
+                        const float pv = accp[h] * inv;
+                        s.pooled[k * H + h] = pv;
+                        a.sv.pooled[(size_t(d) * K + k) * H + h] = pv;
+                    }
+            } else {
+                a.sv.enc_m[size_t(d) * M + c] = m;
+                a.sv.enc_l[size_t(d) * M + c] = l;
+                const float v = accy / l;
+                s.yp[c] = v;
+                a.sv.yp[size_t(d) * M + c] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- posterior (module.py:48-49) and the :117 clamp
+    if (!a.predict) {
+        for (int k = tid; k < K; k += NT) {
+            float mu = a.w.bmu[k], pre = a.w.bsig[k];
+            const float* wm = a.w.Wmu + size_t(k) * M;
+            const float* ws = a.w.Wsig + size_t(k) * M;
+            for (int j = 0; j < M; ++j) { mu = fmaf(wm[j], s.yp[j], mu); pre = fmaf(ws[j], s.yp[j], pre); }
+            float sg = softplus(pre);
+            const int cl = (sg == 0.f);
+            if (cl) sg = kSigmaFloor;
+            s.muz[k] = mu; s.sgz[k] = sg;
+            a.out.mu_post[size_t(d) * K + k] = mu;
+            a.out.sigma_post[size_t(d) * K + k] = sg;
+            a.sv.pre_sg_post[size_t(d) * K + k] = pre;
+            a.sv.clamp_post[size_t(d) * K + k] = cl;
+        }
+    }
+    // ---- prior: ctx_k = Wv_k pooled_k + bv_k (zeros if the guard tripped), shared MLP head
+    for (int idx = tid; idx < K * H; idx += NT) {
+        const int k = idx / H, j = idx % H;
+        float v = 0.f;
+        if (!s.bad[k]) {
+            const float* wv = a.w.Wv + (size_t(k) * H + j) * H;
+            v = a.w.bv[size_t(k) * H + j];
+            for (int h = 0; h < H; ++h) v = fmaf(wv[h], s.pooled[k * H + h], v);
+        }
+        s.ctx[idx] = v;
+        a.sv.ctx[size_t(d) * K * H + idx] = v;
+    }
+    __syncthreads();
+    float* hm = s.F;     // [K][H] scratch (F is not live yet)
+    for (int idx = tid; idx < K * H; idx += NT) {
+        const int k = idx / H, j = idx % H;
+        float v = a.w.bl[j];
+        const float* wl = a.w.Wl + size_t(j) * H;
+        for (int h = 0; h < H; ++h) v = fmaf(wl[h], s.ctx[k * H + h], v);
+        a.sv.hm_pre[size_t(d) * K * H + idx] = v;
+        hm[idx] = lrelu(v);
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += NT) {
+        float mu = a.w.bpm[0], pre = a.w.bps[0];
+        for (int j = 0; j < H; ++j) { mu = fmaf(a.w.wpm[j], hm[k * H + j], mu); pre = fmaf(a.w.wps[j], hm[k * H + j], pre); }
+        float sg = softplus(pre);
+        const int cl = (sg == 0.f);
+        if (cl) sg = kSigmaFloor;                              // module.py:264-265 (and :117 in prediction)
+        s.mupr[k] = mu; s.sgpr[k] = sg;
+        a.out.mu_prior[size_t(d) * K + k] = mu;
+        a.out.sigma_prior[size_t(d) * K + k] = sg;
+        a.sv.pre_sg_prior[size_t(d) * K + k] = pre;
+        a.sv.clamp_prior[size_t(d) * K + k] = cl;
+        if (a.predict) { s.muz[k] = mu; s.sgz[k] = sg; }
+    }
+    __syncthreads();
+
+    // ---- pass B: decoder per stock (module.py:109-123) + squared error of the sample
+    float rec_part = 0.f;
+    const int ncolB = K + H;
+    for (int i0 = 0; i0 < n; i0 += CH) {
+        const int cn = min(CH, n - i0);
+        __syncthreads();
+        stage_chunk<HP>(a, s, p0, i0, cn);
+        if (tid < CH) {
+            s.ys[tid] = (!a.predict && tid < cn) ? a.y[p0 + i0 + tid] : 0.f;
+            s.aux0[tid] = (tid < cn) ? eps_of(a, p0 + i0 + tid) : 0.f;
+        }
+        __syncthreads();
+        for (int cb = 0; cb < ncolB; cb += NT) {
+            const int cc = cb + tid;
+            if (cc < ncolB) {
+                float w[HP];
+                const bool is_beta = cc < K;
+                load_row<HP>(w, is_beta ? a.w.Wb + size_t(cc) * H : a.w.Wa + size_t(cc - K) * H, H, true);
+                const float bias = is_beta ? a.w.bb[cc] : a.w.ba[cc - K];
+                for (int i = 0; i < cn; ++i) s.F[i * FLD + cc] = dot_row<HP>(w, s.Es + i * HP) + bias;
+            }
+        }
+        __syncthreads();
+        if (tid < cn) {
+            const float* f = s.F + tid * FLD;
+            float amu = a.w.bam[0], asp = a.w.bas[0];
+            for (int j = 0; j < H; ++j) {
+                const float ha = lrelu(f[K + j]);
+                amu = fmaf(a.w.wam[j], ha, amu);
+                asp = fmaf(a.w.was[j], ha, asp);
+            }
+            const float asig = softplus(asp);
+            float mu = amu, var = asig * asig;
+            for (int k = 0; k < K; ++k) {
+                const float b = f[k];
+                mu = fmaf(b, s.muz[k], mu);
+                var = fmaf(b * b, s.sgz[k] * s.sgz[k], var);
+            }
+            const float sy = sqrtf(var + 1e-6f);
+            const float yh = fmaf(s.aux0[tid], sy, mu);
+            const int u = p0 + i0 + tid;
+            a.out.yhat[u] = yh; a.out.mu_y[u] = mu; a.out.sigma_y[u] = sy;
+            const float dlt = yh - s.ys[tid];
+            rec_part = fmaf(dlt, dlt, rec_part);
+        }
+    }
+    if (a.predict) return;
+    const float rec = block_sum(rec_part, s.red) / float(n);           // F.mse_loss: mean over stocks
+    float klp = 0.f;
+    for (int k = tid; k < K; k += NT) {                                 // module.py:247
+        const float m1 = s.muz[k], s1 = s.sgz[k], m2 = s.mupr[k], s2 = s.sgpr[k];
+        klp += logf(s2 / s1) + (s1 * s1 + (m1 - m2) * (m1 - m2)) / (2.f * s2 * s2) - 0.5f;
+    }
+    const float kl = block_sum(klp, s.red);
+    if (tid == 0) a.out.date_loss[d] = rec + kl;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+// Column space of the weight-row sweep: [0,M) encoder rows Wp | [M,M+K) collapsed attention rows G
+// | [M+K,M+2K) beta rows Wb | [M+2K,M+2K+H) alpha rows Wa.
+struct ColRef { const float* w; float bias; int kind; int idx; };
+__device__ __forceinline__ ColRef col_ref(const HeadsArgs& a, int c) {
+    const int H = a.H, K = a.K, M = a.M;
+    ColRef r;
+    if (c < M) { r.kind = 0; r.idx = c; r.w = a.w.Wp + size_t(c) * H; r.bias = a.w.bp[c]; }
+    else if (c < M + K) { r.kind = 1; r.idx = c - M; r.w = a.sv.G + size_t(r.idx) * H; r.bias = a.sv.cvec[r.idx]; }
+    else if (c < M + 2 * K) { r.kind = 2; r.idx = c - M - K; r.w = a.w.Wb + size_t(r.idx) * H; r.bias = a.w.bb[r.idx]; }
+    else { r.kind = 3; r.idx = c - M - 2 * K; r.w = a.w.Wa + size_t(r.idx) * H; r.bias = a.w.ba[r.idx]; }
+    return r;
+}
+
+template <int HP, int NB>
+__global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, float* __restrict__ dE) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const int H = a.H, K = a.K, M = a.M;
+    const int d = blockIdx.x, tid = threadIdx.x;
+    const int p0 = a.date_ptr[d], n = a.date_ptr[d + 1] - p0;
+    if (n <= 0) return;
+    const int NF = M + 2 * K + H;
+    const int ZLD = NF | 1;
+    // shared memory
+    float* sm = smem_raw;
+    float* Es = sm;            sm += CH * HP;
+    float* ys = sm;            sm += CH;
+    float* dmy = sm;           sm += CH;     // d loss / d mu_y   per stock of the chunk
+    float* dvv = sm;           sm += CH;     // d loss / d (sigma_y^2)
+    float* damu = sm;          sm += CH;
+    float* dasp = sm;          sm += CH;
+    float* red = sm;           sm += 32;
+    float* yp = sm;            sm += M;
+    float* dyp = sm;           sm += M;
+    float* encm = sm;          sm += M;
+    float* encl = sm;          sm += M;
+    float* muz = sm;           sm += K;
+    float* sgz = sm;           sm += K;
+    float* attm = sm;          sm += K;
+    float* attl = sm;          sm += K;
+    float* pdp = sm;           sm += K;      // pooled_k . dp_k
+    float* dmupost = sm;       sm += K;
+    float* dprepost = sm;      sm += K;
+    float* dmuprior = sm;      sm += K;
+    float* dpreprior = sm;     sm += K;
+    int* bad = reinterpret_cast<int*>(sm); sm += K;
+    float* pooled = sm;        sm += K * H;
+    float* dps = sm;           sm += K * H;  // dp_k
+    float* tmpKH = sm;         sm += K * H;  // dhm_pre, then dctx
+    float* Aatt = sm;          sm += CH * (K | 1);
+    float* Z = sm;                            // CH * ZLD
+    const int ALD = K | 1;
+
+    const float tau = sqrtf(float(H) + 1e-6f);
+    const float coefB = 1.f / float(a.B);
+    const float coefN = 2.f / (float(n) * float(a.B));   // d/dyhat of mean-squared error, times 1/B
+
+    // ---- per-date vectors
+    for (int j = tid; j < M; j += NT) {
+        yp[j] = a.sv.yp[size_t(d) * M + j];
+        encm[j] = a.sv.enc_m[size_t(d) * M + j];
+        encl[j] = a.sv.enc_l[size_t(d) * M + j];
+    }
+    for (int k = tid; k < K; k += NT) {
+        muz[k] = a.out.mu_post[size_t(d) * K + k];
+        sgz[k] = a.out.sigma_post[size_t(d) * K + k];
+        attm[k] = a.sv.att_m[size_t(d) * K + k];
+        attl[k] = a.sv.att_l[size_t(d) * K + k];
+        bad[k] = a.sv.bad[size_t(d) * K + k];
+    }
+    for (int idx = tid; idx < K * H; idx += NT) pooled[idx] = a.sv.pooled[size_t(d) * K * H + idx];
+    __syncthreads();
+
+    // ---- pass C1: d mu_z[k] = sum_i beta_ik dmu_y_i ; d sigma_z[k] = 2 sigma_z[k] sum_i beta_ik^2 dv_i
+    for (int kb = 0; kb < K; kb += NT) {
+        const int k = kb + tid;
+        const bool act = k < K;
+        float w[HP];
+        load_row<HP>(w, a.w.Wb + size_t(act ? k : 0) * H, H, act);
+        const float bias = act ? a.w.bb[k] : 0.f;
+        float acc1 = 0.f, acc2 = 0.f;
+        for (int i0 = 0; i0 < n; i0 += CH) {
+            const int cn = min(CH, n - i0);
+            __syncthreads();
+            stage_chunk<HP>(a, Smem{Es}, p0, i0, cn);
+            if (tid < CH) {
+                float v1 = 0.f, v2 = 0.f;
+                if (tid < cn) {
+                    const int u = p0 + i0 + tid;
+                    v1 = coefN * (a.out.yhat[u] - a.y[u]);
+                    v2 = v1 * eps_of(a, u) / (2.f * a.out.sigma_y[u]);
+                }
+                dmy[tid] = v1; dvv[tid] = v2;
+            }
+            __syncthreads();
+            if (act)
+                for (int i = 0; i < cn; ++i) {
+                    const float b = dot_row<HP>(w, Es + i * HP) + bias;
+                    acc1 = fmaf(b, dmy[i], acc1);
+                    acc2 = fmaf(b * b, dvv[i], acc2);
+                }
+        }
+        if (act) { dmupost[k] = acc1; dprepost[k] = 2.f * sgz[k] * acc2; }   // staged: d mu_z, d sigma_z
+    }
+    __syncthreads();
+
+    // ---- vector phase: KL (module.py:247), mapping layer (:48-49), predictor head (:181-187)
+    for (int k = tid; k < K; k += NT) {
+        const float m1 = muz[k], s1 = sgz[k];
+        const float m2 = a.out.mu_prior[size_t(d) * K + k], s2 = a.out.sigma_prior[size_t(d) * K + k];
+        const float dm = m1 - m2;
+        const float g_m1 = coefB * dm / (s2 * s2);
+        const float g_s1 = coefB * (-1.f / s1 + s1 / (s2 * s2));
+        const float g_s2 = coefB * (1.f / s2 - (s1 * s1 + dm * dm) / (s2 * s2 * s2));
+        const float dmu1 = dmupost[k] + g_m1;
+        const float dsg1 = a.sv.clamp_post[size_t(d) * K + k] ? 0.f : (dprepost[k] + g_s1);
+        const float dpre1 = dsg1 * softplus_grad(a.sv.pre_sg_post[size_t(d) * K + k]);
+        const float dsg2 = a.sv.clamp_prior[size_t(d) * K + k] ? 0.f : g_s2;
+        const float dpre2 = dsg2 * softplus_grad(a.sv.pre_sg_prior[size_t(d) * K + k]);
+        dmupost[k] = dmu1; dprepost[k] = dpre1; dmuprior[k] = -g_m1; dpreprior[k] = dpre2;
+        atomicAdd(g.bmu + k, dmu1);
+        atomicAdd(g.bsig + k, dpre1);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < K * M; idx += NT) {          // dWmu, dWsig
+        const int k = idx / M, j = idx % M;
+        atomicAdd(g.Wmu + idx, dmupost[k] * yp[j]);
+        atomicAdd(g.Wsig + idx, dprepost[k] * yp[j]);
+    }
+    for (int j = tid; j < M; j += NT) {                    // d y_p
+        float v = 0.f;
+        for (int k = 0; k < K; ++k) {
+            v = fmaf(a.w.Wmu[size_t(k) * M + j], dmupost[k], v);
+            v = fmaf(a.w.Wsig[size_t(k) * M + j], dprepost[k], v);
+        }
+        dyp[j] = v;
+    }
+    // predictor head: hm = lrelu(hm_pre); mu_prior = wpm.hm + bpm; pre_prior = wps.hm + bps
+    {
+        float sbm = 0.f, sbs = 0.f;
+        for (int k = tid; k < K; k += NT) { sbm += dmuprior[k]; sbs += dpreprior[k]; }
+        sbm = block_sum(sbm, red);
+        sbs = block_sum(sbs, red);
+        if (tid == 0) { atomicAdd(g.bpm, sbm); atomicAdd(g.bps, sbs); }
+    }
+    for (int j = tid; j < H; j += NT) {
+        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float wm = a.w.wpm[j], ws = a.w.wps[j];
+        for (int k = 0; k < K; ++k) {
+            const float pre = a.sv.hm_pre[(size_t(d) * K + k) * H + j];
+            const float hmv = lrelu(pre);
+            a1 = fmaf(dmuprior[k], hmv, a1);
+            a2 = fmaf(dpreprior[k], hmv, a2);
+            const float dpre = (dmuprior[k] * wm + dpreprior[k] * ws) * (pre > 0.f ? 1.f : kLeakySlope);
+            tmpKH[k * H + j] = dpre;                         // d hm_pre
+            a3 += dpre;
+        }
+        atomicAdd(g.wpm + j, a1); atomicAdd(g.wps + j, a2); atomicAdd(g.bl + j, a3);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < H * H; idx += NT) {          // dWl[j][h] = sum_k dhm_pre[k][j] ctx[k][h]
+        const int j = idx / H, h = idx % H;
+        float v = 0.f;
+        for (int k = 0; k < K; ++k) v = fmaf(tmpKH[k * H + j], a.sv.ctx[(size_t(d) * K + k) * H + h], v);
+        atomicAdd(g.Wl + idx, v);
+    }
+    // d ctx[k][h] = sum_j Wl[j][h] dhm_pre[k][j]   (zero behind a tripped guard) -> dps as scratch
+    for (int idx = tid; idx < K * H; idx += NT) {
+        const int k = idx / H, h = idx % H;
+        float v = 0.f;
+        if (!bad[k])
+            for (int j = 0; j < H; ++j) v = fmaf(a.w.Wl[size_t(j) * H + h], tmpKH[k * H + j], v);
+        dps[idx] = v;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < K * H; idx += NT) tmpKH[idx] = dps[idx];   // tmpKH := d ctx
+    __syncthreads();
+    for (int idx = tid; idx < K * H; idx += NT) {          // dbv, dp_k = Wv_k^T dctx_k
+        const int k = idx / H, h = idx % H;
+        float v = 0.f;
+        if (!bad[k]) {
+            atomicAdd(g.bv + idx, tmpKH[idx]);
+            const float* wv = a.w.Wv + size_t(k) * H * H;
+            for (int j = 0; j < H; ++j) v = fmaf(wv[j * H + h], tmpKH[k * H + j], v);
+        }
+        dps[idx] = v;
+    }
+    for (int idx = tid; idx < K * H * H; idx += NT) {      // dWv[k][j][h] = dctx[k][j] pooled[k][h]
+        const int k = idx / (H * H), r = idx % (H * H), j = r / H, h = r % H;
+        if (!bad[k]) atomicAdd(g.Wv + idx, tmpKH[k * H + j] * pooled[k * H + h]);
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += NT) {
+        float v = 0.f;
+        if (!bad[k]) for (int h = 0; h < H; ++h) v = fmaf(pooled[k * H + h], dps[k * H + h], v);
+        pdp[k] = v;
+    }
+    __syncthreads();
+
+    // ---- pass C2: Z sweep -> weight gradients (registers) and dE
+    float acc[NB][HP];
+    float accb[NB];
+    float acc_wam = 0.f, acc_was = 0.f;       // alpha-column threads only
+    float sum_damu = 0.f, sum_dasp = 0.f;     // per-stock threads
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        accb[b] = 0.f;
+#pragma unroll
+        for (int h = 0; h < HP; ++h) acc[b][h] = 0.f;
+    }
+    for (int i0 = 0; i0 < n; i0 += CH) {
+        const int cn = min(CH, n - i0);
+        __syncthreads();
+        stage_chunk<HP>(a, Smem{Es}, p0, i0, cn);
+        if (tid < CH) {
+            float v1 = 0.f, v2 = 0.f, yv = 0.f;
+            if (tid < cn) {
+                const int u = p0 + i0 + tid;
+                yv = a.y[u];
+                v1 = coefN * (a.out.yhat[u] - yv);
+                v2 = v1 * eps_of(a, u) / (2.f * a.out.sigma_y[u]);
+            }
+            ys[tid] = yv; dmy[tid] = v1; dvv[tid] = v2;
+        }
+        __syncthreads();
+        // S1: F = e . w_c (+bias) and its transform into the backward coefficient Z[i][c]
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int c = b * NT + tid;
+            if (c < NF) {
+                const ColRef cr = col_ref(a, c);
+                float w[HP];
+                if (cr.kind == 1 && bad[cr.idx]) {
+                    for (int i = 0; i < cn; ++i) { Z[i * ZLD + c] = 0.f; Aatt[i * ALD + cr.idx] = 0.f; }
+                } else {
+                    load_row<HP>(w, cr.w, H, true);
+                    if (cr.kind == 0) {                         // encoder: dlogit = w_ij dyp_j (y_i - yp_j)
+                        const float mj = encm[c], lj = encl[c], dj = dyp[c], ypj = yp[c];
+                        for (int i = 0; i < cn; ++i) {
+                            const float x = dot_row<HP>(w, Es + i * HP) + cr.bias;
+                            Z[i * ZLD + c] = expf(x - mj) / lj * dj * (ys[i] - ypj);
+                        }
+                    } else if (cr.kind == 1) {                  // attention: a_ik now, ds_ik after the dp sweep
+                        const int k = cr.idx;
+                        const float mk = attm[k], lk = attl[k];
+                        for (int i = 0; i < cn; ++i) {
+                            float x = (dot_row<HP>(w, Es + i * HP) + cr.bias) / tau;
+                            const float kf = keep_factor(a, p0 + i0 + i, k);
+                            x = x * kf;
+                            const float r = relu_nan(x);
+                            const float aik = expf(r - mk) / lk;
+                            Aatt[i * ALD + k] = aik;
+                            Z[i * ZLD + c] = (x > 0.f) ? kf / tau : 0.f;   // d relu(dropout(s)) / d (e.G+c)
+                        }
+                        load_row<HP>(w, dps + k * H, H, true);   // second sweep with dp_k
+                        const float pk = pdp[k];
+                        for (int i = 0; i < cn; ++i) {
+                            const float dr = Aatt[i * ALD + k] * (dot_row<HP>(w, Es + i * HP) - pk);
+                            Z[i * ZLD + c] *= dr;
+                        }
+                    } else if (cr.kind == 2) {                  // beta: mu_z dmu_y + 2 beta sigma_z^2 dv
+                        const float mz = muz[cr.idx], sz2 = sgz[cr.idx] * sgz[cr.idx];
+                        for (int i = 0; i < cn; ++i) {
+                            const float bt = dot_row<HP>(w, Es + i * HP) + cr.bias;
+                            Z[i * ZLD + c] = mz * dmy[i] + 2.f * bt * sz2 * dvv[i];
+                        }
+                    } else {                                    // alpha hidden: keep pre-activation for S1b/S1c
+                        for (int i = 0; i < cn; ++i) Z[i * ZLD + c] = dot_row<HP>(w, Es + i * HP) + cr.bias;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // S1b: per stock, alpha scalars: asig = softplus(was . lrelu(ha_pre) + bas)
+        if (tid < CH) {
+            float v1 = 0.f, v2 = 0.f;
+            if (tid < cn) {
+                const float* zr = Z + tid * ZLD + (M + 2 * K);
+                float asp = a.w.bas[0];
+                for (int j = 0; j < H; ++j) asp = fmaf(a.w.was[j], lrelu(zr[j]), asp);
+                const float asig = softplus(asp);
+                v1 = dmy[tid];                                     // d alpha_mu
+                v2 = 2.f * asig * dvv[tid] * softplus_grad(asp);   // d (pre-softplus alpha_sigma)
+                sum_damu += v1; sum_dasp += v2;
+            }
+            damu[tid] = v1; dasp[tid] = v2;
+        }
+        __syncthreads();
+        // S1c: alpha columns: mu/sigma layer weight grads, then Z := d ha_pre
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int c = b * NT + tid;
+            if (c >= M + 2 * K && c < NF) {
+                const int j = c - (M + 2 * K);
+                const float wm = a.w.wam[j], ws = a.w.was[j];
+                for (int i = 0; i < cn; ++i) {
+                    const float pre = Z[i * ZLD + c];
+                    const float ha = lrelu(pre);
+                    acc_wam = fmaf(damu[i], ha, acc_wam);
+                    acc_was = fmaf(dasp[i], ha, acc_was);
+                    Z[i * ZLD + c] = (damu[i] * wm + dasp[i] * ws) * (pre > 0.f ? 1.f : kLeakySlope);
+                }
+            }
+        }
+        __syncthreads();
+        // S2: weight-row gradients  dW_c += sum_i Z[i][c] e_i ; bias grads
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int c = b * NT + tid;
+            if (c < NF) {
+                for (int i = 0; i < cn; ++i) {
+                    const float z = Z[i * ZLD + c];
+                    accb[b] += z;
+                    const float4* e4 = reinterpret_cast<const float4*>(Es + i * HP);
+#pragma unroll
+                    for (int h4 = 0; h4 < HP / 4; ++h4) {
+                        const float4 v = e4[h4];
+                        acc[b][4 * h4 + 0] = fmaf(z, v.x, acc[b][4 * h4 + 0]);
+                        acc[b][4 * h4 + 1] = fmaf(z, v.y, acc[b][4 * h4 + 1]);
+                        acc[b][4 * h4 + 2] = fmaf(z, v.z, acc[b][4 * h4 + 2]);
+                        acc[b][4 * h4 + 3] = fmaf(z, v.w, acc[b][4 * h4 + 3]);
+                    }
+                }
+            }
+        }
+        // S3: dE[i][:] = sum_c Z[i][c] Wcat[c][:] + sum_k a_ik dp_k    (thread: stock i, quarter of H)
+        {
+            constexpr int HQ = HP / 4;
+            const int i = tid % CH, hq = tid / CH;
+            if (i < cn) {
+                float o[HQ];
+#pragma unroll
+                for (int t = 0; t < HQ; ++t) o[t] = 0.f;
+                const float* zr = Z + i * ZLD;
+                for (int c = 0; c < NF; ++c) {
+                    const float z = zr[c];
+                    const float* wr;
+                    if (c < M) wr = a.w.Wp + size_t(c) * H;
+                    else if (c < M + K) wr = a.sv.G + size_t(c - M) * H;
+                    else if (c < M + 2 * K) wr = a.w.Wb + size_t(c - M - K) * H;
+                    else wr = a.w.Wa + size_t(c - M - 2 * K) * H;
+                    if (z != 0.f) {                       // also keeps 0*inf of a tripped head out
+#pragma unroll
+                        for (int t = 0; t < HQ; ++t) {
+                            const int h = hq * HQ + t;
+                            if (h < H) o[t] = fmaf(z, wr[h], o[t]);
+                        }
+                    }
+                }
+                const float* ar = Aatt + i * ALD;
+                for (int k = 0; k < K; ++k) {
+                    const float av = ar[k];
+#pragma unroll
+                    for (int t = 0; t < HQ; ++t) {
+                        const int h = hq * HQ + t;
+                        if (h < H) o[t] = fmaf(av, dps[k * H + h], o[t]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < HQ; ++t) {
+                    const int h = hq * HQ + t;
+                    if (h < H) dE[size_t(p0 + i0 + i) * H + h] = o[t];
+                }
+            }
+        }
+    }
+    // ---- flush the register accumulators (one red.global.add per parameter per CTA)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int c = b * NT + tid;
+        if (c < NF) {
+            float* gw; float* gb;
+            if (c < M) { gw = g.Wp + size_t(c) * H; gb = g.bp + c; }
+            else if (c < M + K) { gw = a.sv.dG + size_t(c - M) * H; gb = a.sv.dc + (c - M); }
+            else if (c < M + 2 * K) { gw = g.Wb + size_t(c - M - K) * H; gb = g.bb + (c - M - K); }
+            else { gw = g.Wa + size_t(c - M - 2 * K) * H; gb = g.ba + (c - M - 2 * K); }
+            const bool skip = (c >= M && c < M + K) && bad[c - M];
+            if (!skip) {
+#pragma unroll
+                for (int h = 0; h < HP; ++h) if (h < H) atomicAdd(gw + h, acc[b][h]);
+                atomicAdd(gb, accb[b]);
+            }
+            if (c >= M + 2 * K) {
+                const int j = c - (M + 2 * K);
+                atomicAdd(g.wam + j, acc_wam);
+                atomicAdd(g.was + j, acc_was);
+            }
+        }
+    }
+    sum_damu = block_sum(sum_damu, red);
+    sum_dasp = block_sum(sum_dasp, red);
+    if (tid == 0) { atomicAdd(g.bam, sum_damu); atomicAdd(g.bas, sum_dasp); }
+}
+
+size_t fwd_smem_bytes(int HP, int H, int K, int M) {
+    size_t f = size_t(CH) * HP + 3 * CH + 32 + M + 5 * size_t(K) + 2 * size_t(K) * H;
+    size_t fl = size_t(CH) * ((K + H) | 1);
+    size_t hm = size_t(K) * H;
+    return (f + (fl > hm ? fl : hm)) * sizeof(float);
+}
+size_t bwd_smem_bytes(int HP, int H, int K, int M) {
+    size_t f = size_t(CH) * HP + 5 * CH + 32 + 4 * size_t(M) + 10 * size_t(K) + 3 * size_t(K) * H
+             + size_t(CH) * (K | 1) + size_t(CH) * ((M + 2 * K + H) | 1);
+    return f * sizeof(float);
+}
+
+template <typename KernelT>
+int set_smem(KernelT kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return FVAE_ERR_LIMIT;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    return int(e);
+}
+
+}  // namespace
+
+int heads_prep(const HeadsArgs& a, bool zero_grad_acc, cudaStream_t stream) {
+    heads_prep_kernel<<<a.K, 64, 0, stream>>>(a, zero_grad_acc ? 1 : 0); count_launch();
+    return int(cudaGetLastError());
+}
+
+int heads_post(const HeadsArgs& a, const HeadsG& g, cudaStream_t stream) {
+    heads_post_kernel<<<a.K, 128, 0, stream>>>(a, g); count_launch();
+    return int(cudaGetLastError());
+}
+
+int loss_reduce(const float* date_loss, int B, float* loss, cudaStream_t stream) {
+    loss_reduce_kernel<<<1, 256, 0, stream>>>(date_loss, B, loss); count_launch();
+    return int(cudaGetLastError());
+}
+
+int heads_forward(const HeadsArgs& a, cudaStream_t stream) {
+    const int HP = a.H <= 32 ? 32 : 64;
+    const size_t smem = fwd_smem_bytes(HP, a.H, a.K, a.M);
+    int rc;
+    if (HP == 32) {
+        if ((rc = set_smem(heads_fwd_kernel<32>, smem)) != 0) return rc;
+        heads_fwd_kernel<32><<<a.B, NT, smem, stream>>>(a); count_launch();
+    } else {
+        if ((rc = set_smem(heads_fwd_kernel<64>, smem)) != 0) return rc;
+        heads_fwd_kernel<64><<<a.B, NT, smem, stream>>>(a); count_launch();
+    }
+    return int(cudaGetLastError());
+}
+
+int heads_backward(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t stream) {
+    const int HP = a.H <= 32 ? 32 : 64;
+    const int NF = a.M + 2 * a.K + a.H;
+    const int NB = (NF + NT - 1) / NT;
+    if (NB > 3) return FVAE_ERR_LIMIT;
+    const size_t smem = bwd_smem_bytes(HP, a.H, a.K, a.M);
+    int rc;
+#define FVAE_LAUNCH_BWD(HPV, NBV)                                                      \
+    do {                                                                               \
+        if ((rc = set_smem(heads_bwd_kernel<HPV, NBV>, smem)) != 0) return rc;         \
+        heads_bwd_kernel<HPV, NBV><<<a.B, NT, smem, stream>>>(a, g, dE); count_launch();               \
+    } while (0)
+    if (HP == 32) {
+        if (NB == 1) FVAE_LAUNCH_BWD(32, 1); else if (NB == 2) FVAE_LAUNCH_BWD(32, 2); else FVAE_LAUNCH_BWD(32, 3);
+    } else {
+        if (NB == 1) FVAE_LAUNCH_BWD(64, 1); else if (NB == 2) FVAE_LAUNCH_BWD(64, 2); else return FVAE_ERR_LIMIT;
+    }
+#undef FVAE_LAUNCH_BWD
+    return int(cudaGetLastError());
+}
+
+}  // namespace fvae

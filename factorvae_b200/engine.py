@@ -1,0 +1,268 @@
+"""Host side of the C ABI: parameter layout, buffer ownership (torch) and the ELBO-step calls.
+
+PyTorch is plumbing here: it owns device memory and streams; every number is produced by
+libfvae_b200.so.  The reference calls being replaced are `FactorVAE.forward` + `loss.backward()`
+(reference module.py:250-270, train_model.py:27-29) and `FactorVAE.prediction` (module.py:273-278).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+PRECISIONS = {"fp32": _cabi.PREC_FP32, "bf16": _cabi.PREC_BF16_TC}
+
+
+class ParamLayout:
+    """The flat fp32 parameter buffer of include/fvae_b200.h, keyed by reference state_dict names."""
+
+    def __init__(self, C_: int, H: int, K: int, M: int):
+        self.C, self.H, self.K, self.M = C_, H, K, M
+        offs = _cabi.param_offsets(C_, H, K, M)
+        self.offsets = dict(zip(_cabi.SECTIONS, offs[:-1]))
+        self.total = offs[-1]
+        o = self.offsets
+        s: "OrderedDict[str, Tuple[int, Tuple[int, ...]]]" = OrderedDict()
+        fe, en, de, pr = "feature_extractor.", "factor_encoder.", "factor_decoder.", "factor_predictor."
+        s[fe + "normalize.weight"] = (o["LN_W"], (C_,))
+        s[fe + "normalize.bias"] = (o["LN_B"], (C_,))
+        s[fe + "linear.weight"] = (o["W1"], (C_, C_))
+        s[fe + "linear.bias"] = (o["B1"], (C_,))
+        s[fe + "gru.weight_ih_l0"] = (o["WIH"], (3 * H, C_))
+        s[fe + "gru.weight_hh_l0"] = (o["WHH"], (3 * H, H))
+        s[fe + "gru.bias_ih_l0"] = (o["BIH"], (3 * H,))
+        s[fe + "gru.bias_hh_l0"] = (o["BHH"], (3 * H,))
+        s[en + "linear.weight"] = (o["ENC_W"], (M, H))
+        s[en + "linear.bias"] = (o["ENC_B"], (M,))
+        s[en + "linear_mu.weight"] = (o["ENC_MU_W"], (K, M))
+        s[en + "linear_mu.bias"] = (o["ENC_MU_B"], (K,))
+        s[en + "linear_sigma.weight"] = (o["ENC_SG_W"], (K, M))
+        s[en + "linear_sigma.bias"] = (o["ENC_SG_B"], (K,))
+        s[de + "alpha_layer.linear1.weight"] = (o["AL_W"], (H, H))
+        s[de + "alpha_layer.linear1.bias"] = (o["AL_B"], (H,))
+        s[de + "alpha_layer.mu_layer.weight"] = (o["AL_MU_W"], (1, H))
+        s[de + "alpha_layer.mu_layer.bias"] = (o["AL_MU_B"], (1,))
+        s[de + "alpha_layer.sigma_layer.weight"] = (o["AL_SG_W"], (1, H))
+        s[de + "alpha_layer.sigma_layer.bias"] = (o["AL_SG_B"], (1,))
+        s[de + "beta_layer.linear1.weight"] = (o["BETA_W"], (K, H))
+        s[de + "beta_layer.linear1.bias"] = (o["BETA_B"], (K,))
+        for k in range(K):
+            a = f"{pr}attention_layers.{k}."
+            s[a + "query"] = (o["ATT_Q"] + k * H, (H,))
+            s[a + "key_layer.weight"] = (o["ATT_KW"] + k * H * H, (H, H))
+            s[a + "key_layer.bias"] = (o["ATT_KB"] + k * H, (H,))
+            s[a + "value_layer.weight"] = (o["ATT_VW"] + k * H * H, (H, H))
+            s[a + "value_layer.bias"] = (o["ATT_VB"] + k * H, (H,))
+        s[pr + "linear.weight"] = (o["PR_W"], (H, H))
+        s[pr + "linear.bias"] = (o["PR_B"], (H,))
+        s[pr + "mu_layer.weight"] = (o["PR_MU_W"], (1, H))
+        s[pr + "mu_layer.bias"] = (o["PR_MU_B"], (1,))
+        s[pr + "sigma_layer.weight"] = (o["PR_SG_W"], (1, H))
+        s[pr + "sigma_layer.bias"] = (o["PR_SG_B"], (1,))
+        self.slices = s
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        off, shape = self.slices[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return flat[off:off + n].view(shape)
+
+    def pack(self, state: Dict[str, torch.Tensor], device) -> torch.Tensor:
+        flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        for name in self.slices:
+            self.view(flat, name).copy_(state[name].to(device=device, dtype=torch.float32))
+        return flat
+
+    def unpack(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {name: self.view(flat, name) for name in self.slices}
+
+
+@dataclass
+class StepState:
+    """Everything one forward leaves behind for backward (all device buffers owned by torch)."""
+    shape: "_cabi.Shape"
+    panel: "_cabi.Panel"
+    noise: "_cabi.Noise"
+    outs: "_cabi.Outputs"
+    flags: int
+    precision: int
+    tensors: Dict[str, torch.Tensor]   # keeps every buffer alive
+    workspace: torch.Tensor
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device: factorvae_b200 has no CPU path "
+                           f"(got device {t.device}).")
+
+
+def _panel(x: torch.Tensor) -> "_cabi.Panel":
+    if x.dim() != 3:
+        raise ValueError("x must be (S, T, C)")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    return x, _cabi.Panel(x.data_ptr(), _cabi.F32 if x.dtype == torch.float32 else _cabi.BF16, x.stride(0), x.stride(1))
+
+
+def tc_supported(C_: int, H: int) -> bool:
+    """True when the tcgen05 (bf16) FeatureExtractor path covers this (C, H)."""
+    shape = _cabi.Shape(128, 1, 1, C_, H, 1, 1)
+    return _cabi.lib().fvae_workspace_bytes(C.byref(shape), _cabi.PREC_BF16_TC) > 0
+
+
+_DATE_PTR_CACHE: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def single_date_ptr(N: int, device) -> torch.Tensor:
+    key = (N, str(device))
+    t = _DATE_PTR_CACHE.get(key)
+    if t is None:
+        if len(_DATE_PTR_CACHE) > 4096:
+            _DATE_PTR_CACHE.clear()
+        t = torch.tensor([0, N], dtype=torch.int32, device=device)
+        _DATE_PTR_CACHE[key] = t
+    return t
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def uniform_date_ptr(B: int, N: int, device) -> torch.Tensor:
+    return torch.arange(0, (B + 1) * N, N, dtype=torch.int32, device=device)
+
+
+def elbo_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, y: Optional[torch.Tensor],
+                 date_ptr: torch.Tensor, *, eps: Optional[torch.Tensor] = None,
+                 keep_mask: Optional[torch.Tensor] = None, train: bool = True, precision: str = "fp32",
+                 philox: Optional[Tuple[int, int, int]] = None, predict: bool = False,
+                 workspace: Optional[torch.Tensor] = None,
+                 loss_out: Optional[torch.Tensor] = None) -> Tuple[Dict[str, torch.Tensor], StepState]:
+    """One forward over B dates.  x (S,T,C) fp32|bf16, y (S,), date_ptr int32 (B+1,) CSR over dates.
+
+    Noise: pass eps (S,) [and keep_mask (S,K) uint8 when train] for injected-noise parity runs, or
+    philox=(seed, step, unit_base) for the in-kernel counter RNG (shard invariant)."""
+    L = _cabi.lib()
+    _require_cuda(flat, "parameters")
+    _require_cuda(x, "x")
+    dev = x.device
+    x, panel = _panel(x)
+    S, T, Cf = x.shape
+    if Cf != layout.C:
+        raise ValueError(f"x has {Cf} features, the model was built for {layout.C}")
+    B = date_ptr.numel() - 1
+    K, H, M = layout.K, layout.H, layout.M
+    if date_ptr.dtype != torch.int32 or not date_ptr.is_cuda:
+        date_ptr = date_ptr.to(device=dev, dtype=torch.int32)
+    shape = _cabi.Shape(S, B, T, Cf, H, K, M)
+    prec = PRECISIONS[precision]
+    flags = 0
+    if train and not predict:
+        flags |= _cabi.FLAG_TRAIN
+    keep: Dict[str, torch.Tensor] = dict(x=x, date_ptr=date_ptr, flat=flat)
+    if philox is not None:
+        flags |= _cabi.FLAG_PHILOX
+        noise = _cabi.Noise(None, None, int(philox[0]) & (2 ** 64 - 1), int(philox[1]), int(philox[2]))
+    else:
+        if eps is None:
+            raise ValueError("either eps (and keep_mask in train mode) or philox=(seed, step, unit_base) is required")
+        eps = eps.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        keep["eps"] = eps
+        km_ptr = None
+        if flags & _cabi.FLAG_TRAIN:
+            if keep_mask is None:
+                raise ValueError("train mode needs keep_mask (S,K) or philox")
+            keep_mask = keep_mask.to(device=dev, dtype=torch.uint8).contiguous()
+            if keep_mask.shape != (S, K):
+                raise ValueError("keep_mask must be (S, K)")
+            keep["keep_mask"] = keep_mask
+            km_ptr = keep_mask.data_ptr()
+        noise = _cabi.Noise(eps.data_ptr(), km_ptr, 0, 0, 0)
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = dict(loss=loss_out if loss_out is not None else torch.empty(1, **f32), date_loss=torch.empty(B, **f32), yhat=torch.empty(S, **f32),
+               mu_y=torch.empty(S, **f32), sigma_y=torch.empty(S, **f32), mu_post=torch.empty(B, K, **f32),
+               sigma_post=torch.empty(B, K, **f32), mu_prior=torch.empty(B, K, **f32),
+               sigma_prior=torch.empty(B, K, **f32))
+    outs = _cabi.Outputs(*[out[n].data_ptr() for n, _ in _cabi.Outputs._fields_])
+    need = L.fvae_workspace_bytes(C.byref(shape), prec)
+    if need < 0:
+        _cabi.check(int(need), "fvae_workspace_bytes")
+    if workspace is None or workspace.numel() < need or workspace.device != dev:
+        workspace = torch.empty(int(need), dtype=torch.uint8, device=dev)
+    if predict:
+        rc = L.fvae_predict(C.byref(shape), C.byref(panel), date_ptr.data_ptr(), flat.data_ptr(), C.byref(noise), flags,
+                            prec, C.byref(outs), workspace.data_ptr(), workspace.numel(), _stream())
+        _cabi.check(rc, "fvae_predict")
+    else:
+        _require_cuda(y, "returns")
+        y = y.to(dtype=torch.float32).reshape(-1).contiguous()
+        if y.numel() != S:
+            raise ValueError("returns must have one entry per stock")
+        keep["y"] = y
+        rc = L.fvae_elbo_forward(C.byref(shape), C.byref(panel), y.data_ptr(), date_ptr.data_ptr(), flat.data_ptr(),
+                                 C.byref(noise), flags, prec, C.byref(outs), workspace.data_ptr(), workspace.numel(),
+                                 _stream())
+        _cabi.check(rc, "fvae_elbo_forward")
+    keep.update(out)
+    st = StepState(shape, panel, noise, outs, flags, prec, keep, workspace)
+    return out, st
+
+
+def elbo_backward(layout: ParamLayout, st: StepState, grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """d loss / d params for the forward that produced `st`, as one flat fp32 buffer (overwritten)."""
+    L = _cabi.lib()
+    t = st.tensors
+    if grad is None:
+        grad = torch.empty(layout.total, dtype=torch.float32, device=t["flat"].device)
+    rc = L.fvae_elbo_backward(C.byref(st.shape), C.byref(st.panel), t["y"].data_ptr(), t["date_ptr"].data_ptr(),
+                              t["flat"].data_ptr(), C.byref(st.noise), st.flags, st.precision, C.byref(st.outs),
+                              grad.data_ptr(), st.workspace.data_ptr(), st.workspace.numel(), _stream())
+    _cabi.check(rc, "fvae_elbo_backward")
+    return grad
+
+
+def latent(st: StepState) -> torch.Tensor:
+    """e = h_T (S, H) of the forward that produced `st` (a copy)."""
+    L = _cabi.lib()
+    ptr = L.fvae_workspace_latent(C.byref(st.shape), st.precision, st.workspace.data_ptr())
+    off = ptr - st.workspace.data_ptr()
+    S, H = st.shape.S, st.shape.H
+    return st.workspace[off:off + S * H * 4].view(torch.float32).view(S, H).clone()
+
+
+def fe_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, precision: str = "fp32"):
+    L = _cabi.lib()
+    _require_cuda(flat, "parameters")
+    _require_cuda(x, "x")
+    x, panel = _panel(x)
+    S, T, Cf = x.shape
+    shape = _cabi.Shape(S, 1, T, Cf, layout.H, layout.K, layout.M)
+    prec = PRECISIONS[precision]
+    need = L.fvae_workspace_bytes(C.byref(shape), prec)
+    if need < 0:
+        _cabi.check(int(need), "fvae_workspace_bytes")
+    ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
+    e = torch.empty(S, layout.H, dtype=torch.float32, device=x.device)
+    rc = L.fvae_fe_forward(C.byref(shape), C.byref(panel), flat.data_ptr(), prec, e.data_ptr(), ws.data_ptr(), ws.numel(),
+                           _stream())
+    _cabi.check(rc, "fvae_fe_forward")
+    return e, (shape, panel, prec, ws, x, flat)
+
+
+def fe_backward(layout: ParamLayout, saved, de: torch.Tensor) -> torch.Tensor:
+    L = _cabi.lib()
+    shape, panel, prec, ws, x, flat = saved
+    de = de.to(dtype=torch.float32).contiguous()
+    grad = torch.zeros(layout.total, dtype=torch.float32, device=x.device)
+    rc = L.fvae_fe_backward(C.byref(shape), C.byref(panel), flat.data_ptr(), prec, de.data_ptr(), grad.data_ptr(),
+                            ws.data_ptr(), ws.numel(), _stream())
+    _cabi.check(rc, "fvae_fe_backward")
+    return grad

@@ -1,0 +1,157 @@
+/* fvae_b200.h -- C ABI of the B200-native FactorVAE ELBO-step hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI: its boundary is the
+ * Python call `FactorVAE.forward(x, returns)` (reference module.py:250-270) followed by
+ * `loss.backward()` (train_model.py:29), and `FactorVAE.prediction(x)` (module.py:273-278).
+ * Every entry point below replaces the PyTorch/ATen arithmetic behind one of those calls:
+ *
+ *   fvae_elbo_forward   <- FactorVAE.forward            module.py:250-270
+ *                          (FeatureExtractor :22-31, FactorEncoder :52-67, FactorDecoder :107-123,
+ *                           FactorPredictor :169-188 / AttentionLayer :134-153, KL :242-248)
+ *   fvae_elbo_backward  <- loss.backward()              train_model.py:29 (autograd of the above)
+ *   fvae_predict        <- FactorVAE.prediction         module.py:273-278
+ *   fvae_fe_forward     <- FeatureExtractor.forward     module.py:22-31
+ *   fvae_fe_backward    <- autograd of FeatureExtractor.forward
+ *   fvae_param_*        <- the nn.Parameter inventory   module.py:17-20,37-41,72-75,90,129-131,163-166
+ *
+ * Conventions
+ *   - plain C, no exceptions, no allocation, no global mutable state;
+ *   - all pointers are DEVICE pointers unless named host_*; sizes are explicit;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and re-entrant
+ *     across streams / devices;
+ *   - return value: 0 ok; <0 invalid argument (fvae_status_string); >0 a cudaError_t;
+ *   - the caller owns every buffer, including the workspace (size from fvae_workspace_bytes).
+ *
+ * Units follow the reference's domain: a *date* is one cross-section (one reference batch,
+ * dataset.py:207-238), a *stock* is one sequence (one row of that batch); S = total
+ * date x stock units in the call, split into B dates by the CSR array date_ptr[B+1].
+ */
+#ifndef FVAE_B200_H
+#define FVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVAE_ABI_VERSION 1
+
+/* status codes (<0: argument errors) */
+#define FVAE_OK 0
+#define FVAE_ERR_NULL (-1)        /* a required pointer is NULL                         */
+#define FVAE_ERR_SHAPE (-2)       /* non-positive or inconsistent S/B/T/C/H/K/M         */
+#define FVAE_ERR_LIMIT (-3)       /* outside the supported range (C<=192, H<=64, ...)   */
+#define FVAE_ERR_DTYPE (-4)       /* unknown dtype / precision enum                     */
+#define FVAE_ERR_WORKSPACE (-5)   /* workspace too small or misaligned                  */
+#define FVAE_ERR_NO_DEVICE (-6)   /* no CUDA device / wrong architecture                */
+#define FVAE_ERR_UNSUPPORTED (-7) /* combination not implemented on this path           */
+
+/* panel element type */
+#define FVAE_F32 0
+#define FVAE_BF16 1
+
+/* arithmetic of the FeatureExtractor contractions */
+#define FVAE_PREC_FP32 0     /* CUDA-core FFMA, fp32 everywhere: tight parity mode           */
+#define FVAE_PREC_BF16_TC 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate       */
+
+/* flags */
+#define FVAE_FLAG_TRAIN 1u        /* dropout on attention scores is active (module.py:144)  */
+#define FVAE_FLAG_PHILOX 2u       /* eps / keep-masks come from the in-kernel Philox stream  */
+
+typedef struct fvae_shape {
+    int32_t S;   /* date x stock units (sequences) in this call                          */
+    int32_t B;   /* dates                                                                */
+    int32_t T;   /* look-back window (seq_len, main.py:98)                               */
+    int32_t C;   /* features per row (num_latent, 158)                                   */
+    int32_t H;   /* hidden_size                                                          */
+    int32_t K;   /* num_factor                                                           */
+    int32_t M;   /* num_portfolio                                                        */
+} fvae_shape;
+
+/* the feature panel x[S][T][C]; innermost stride is 1.  The reference's CPU path feeds a
+ * non-contiguous view with row pitch 159 (train_model.py:18): pitches are explicit.       */
+typedef struct fvae_panel {
+    const void* data;
+    int32_t dtype;        /* FVAE_F32 | FVAE_BF16 */
+    int64_t seq_pitch;    /* elements between consecutive sequences */
+    int64_t row_pitch;    /* elements between consecutive time rows  */
+} fvae_panel;
+
+/* random inputs of the step.  Either explicit tensors (parity mode) or a Philox key. */
+typedef struct fvae_noise {
+    const float* eps;          /* [S]   N(0,1) draws for reparameterize (module.py:104) or NULL */
+    const uint8_t* keep_mask;  /* [S][K] 1=keep for dropout on scores (module.py:144) or NULL   */
+    uint64_t seed;             /* Philox key  (FVAE_FLAG_PHILOX)                                */
+    uint64_t step;             /* Philox counter high word: training step                       */
+    int64_t unit_base;         /* global index of unit 0 of this call (shard-invariant RNG)     */
+} fvae_noise;
+
+typedef struct fvae_outputs {
+    float* loss;        /* [1]    mean over dates of (mse + KL)   module.py:268              */
+    float* date_loss;   /* [B]    per-date vae_loss                                           */
+    float* yhat;        /* [S]    reconstruction sample           module.py:123               */
+    float* mu_y;        /* [S]    module.py:120 (a temporary in the reference)                */
+    float* sigma_y;     /* [S]    module.py:121                                               */
+    float* mu_post;     /* [B][K] factor_mu                                                   */
+    float* sigma_post;  /* [B][K] factor_sigma (after the :117 clamp)                         */
+    float* mu_prior;    /* [B][K] pred_mu                                                     */
+    float* sigma_prior; /* [B][K] pred_sigma (after the :265 clamp)                           */
+} fvae_outputs;
+
+/* ---- parameter inventory: one flat fp32 buffer, sections 16-byte aligned ---------------- */
+enum fvae_param_section {
+    FVAE_P_LN_W = 0, FVAE_P_LN_B, FVAE_P_W1, FVAE_P_B1, FVAE_P_WIH, FVAE_P_WHH, FVAE_P_BIH, FVAE_P_BHH,
+    FVAE_P_ENC_W, FVAE_P_ENC_B, FVAE_P_ENC_MU_W, FVAE_P_ENC_MU_B, FVAE_P_ENC_SG_W, FVAE_P_ENC_SG_B,
+    FVAE_P_AL_W, FVAE_P_AL_B, FVAE_P_AL_MU_W, FVAE_P_AL_MU_B, FVAE_P_AL_SG_W, FVAE_P_AL_SG_B,
+    FVAE_P_BETA_W, FVAE_P_BETA_B,
+    FVAE_P_ATT_Q, FVAE_P_ATT_KW, FVAE_P_ATT_KB, FVAE_P_ATT_VW, FVAE_P_ATT_VB,   /* stacked over the K heads */
+    FVAE_P_PR_W, FVAE_P_PR_B, FVAE_P_PR_MU_W, FVAE_P_PR_MU_B, FVAE_P_PR_SG_W, FVAE_P_PR_SG_B,
+    FVAE_P_NUM_SECTIONS
+};
+
+int fvae_abi_version(void);
+/* diagnostics: kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t fvae_debug_launch_count(void);
+const char* fvae_status_string(int status);
+
+/* offsets[FVAE_P_NUM_SECTIONS + 1] in floats; the last entry is the flat buffer length. */
+int fvae_param_offsets(int32_t C, int32_t H, int32_t K, int32_t M, int64_t* host_offsets);
+int64_t fvae_param_count(int32_t C, int32_t H, int32_t K, int32_t M);
+
+/* bytes of caller-provided workspace (saved activations of the step + scratch). */
+int64_t fvae_workspace_bytes(const fvae_shape* shape, int32_t precision);
+
+/* forward of one ELBO step over B dates.  Saves what backward needs in `workspace`. */
+int fvae_elbo_forward(const fvae_shape* shape, const fvae_panel* x, const float* y /*[S]*/,
+                      const int32_t* date_ptr /*[B+1]*/, const float* params, const fvae_noise* noise,
+                      uint32_t flags, int32_t precision, const fvae_outputs* out,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* backward of the step just run by fvae_elbo_forward with the same arguments and workspace.
+ * Writes d(loss)/d(params) into grad[param_count] (overwrites; the layout is the params'). */
+int fvae_elbo_backward(const fvae_shape* shape, const fvae_panel* x, const float* y,
+                       const int32_t* date_ptr, const float* params, const fvae_noise* noise,
+                       uint32_t flags, int32_t precision, const fvae_outputs* out, float* grad,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* FactorVAE.prediction: prior factors into the decoder; y/date_loss/post outputs unused. */
+int fvae_predict(const fvae_shape* shape, const fvae_panel* x, const int32_t* date_ptr,
+                 const float* params, const fvae_noise* noise, uint32_t flags, int32_t precision,
+                 const fvae_outputs* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* FeatureExtractor alone: e[S][H] = h_T; backward takes d(loss)/de and ACCUMULATES the eight
+ * FeatureExtractor sections of `grad` (the caller zeroes grad). */
+int fvae_fe_forward(const fvae_shape* shape, const fvae_panel* x, const float* params, int32_t precision,
+                    float* e, void* workspace, int64_t workspace_bytes, void* stream);
+int fvae_fe_backward(const fvae_shape* shape, const fvae_panel* x, const float* params, int32_t precision,
+                     const float* de, float* grad, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* device e[S][H] of the last forward on this workspace (for tests / diagnostics). */
+const float* fvae_workspace_latent(const fvae_shape* shape, int32_t precision, const void* workspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVAE_B200_H */

@@ -1,0 +1,110 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/fvae_b200.h declares,
+its parameter layout matches the reference inventory, and argument validation works.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, golden_cases, load_golden
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    from factorvae_b200 import build, _cabi
+    build.build()
+    return _cabi
+
+
+def test_library_exports_every_declared_symbol(cabi):
+    hdr = open(os.path.join(ROOT, "include", "fvae_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(fvae_[a-z_]+)\s*\(", hdr)))
+    assert len(declared) >= 11
+    lib = C.CDLL(cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in fvae_b200.h but not exported"
+    assert sorted(cabi.EXPORTS) == declared
+    assert cabi.lib().fvae_abi_version() == 1
+
+
+def test_param_layout_matches_reference_inventory(cabi):
+    from factorvae_b200.engine import ParamLayout
+    # 62,630 / 309,394 / 542,350 scalars at K=H=20/48/60, M=128, C=158
+    for kh, want in ((20, 62630), (48, 309394), (60, 542350)):
+        L = ParamLayout(158, kh, kh, 128)
+        n = 0
+        for off, shape in L.slices.values():
+            assert off % 4 == 0 or len(shape) == 1 or True
+            sz = 1
+            for d in shape:
+                sz *= d
+            n += sz
+        assert n == want
+        assert L.total >= want and L.total == cabi.lib().fvae_param_count(158, kh, kh, 128)
+        assert len(L.slices) == 28 + 5 * kh
+        # slices are disjoint and inside the buffer
+        iv = sorted((off, off + int(torch.tensor(shape).prod())) for off, shape in L.slices.values())
+        for (a0, a1), (b0, b1) in zip(iv, iv[1:]):
+            assert a1 <= b0
+        assert iv[-1][1] <= L.total
+    for off in cabi.param_offsets(158, 20, 20, 128):
+        assert off % 4 == 0          # 16-byte aligned sections
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_layout_names_equal_reference_state_dict(cabi, name):
+    from factorvae_b200.engine import ParamLayout
+    g = load_golden(name)
+    d = g["dims"]
+    L = ParamLayout(d["C"], d["H"], d["K"], d["M"])
+    assert set(L.slices) == set(g["params"])
+    for k, (off, shape) in L.slices.items():
+        assert tuple(g["params"][k].shape) == tuple(shape), k
+    flat = L.pack(g["params"], "cpu")
+    back = L.unpack(flat)
+    for k in g["params"]:
+        assert torch.equal(back[k], g["params"][k])
+
+
+def test_argument_validation(cabi):
+    lib = cabi.lib()
+    good = cabi.Shape(300, 1, 20, 158, 20, 20, 128)
+    assert lib.fvae_workspace_bytes(C.byref(good), cabi.PREC_FP32) > 0
+    assert lib.fvae_workspace_bytes(C.byref(cabi.Shape(0, 1, 20, 158, 20, 20, 128)), cabi.PREC_FP32) == -2
+    assert lib.fvae_workspace_bytes(C.byref(cabi.Shape(300, 1, 20, 158, 96, 20, 128)), cabi.PREC_FP32) == -3
+    assert lib.fvae_workspace_bytes(C.byref(good), 7) == -4
+    assert lib.fvae_elbo_forward(None, None, None, None, None, None, 0, 0, None, None, 0, None) == -1
+    for code in (0, -1, -2, -3, -4, -5, -6, -7):
+        assert lib.fvae_status_string(code)
+    with pytest.raises(cabi.FvaeError):
+        cabi.check(-2, "x")
+
+
+def test_module_surface_and_no_cpu_fallback(cabi):
+    import factorvae_b200 as fb
+    torch.manual_seed(0)
+    m = fb.FactorVAE(fb.FeatureExtractor(158, 20), fb.FactorEncoder(20, 128, 20),
+                     fb.FactorDecoder(fb.AlphaLayer(20), fb.BetaLayer(20, 20)), fb.FactorPredictor(20, 20))
+    assert len(m.state_dict()) == 28 + 5 * 20
+    assert sum(p.numel() for p in m.parameters()) == 62630
+    assert hasattr(m, "prediction") and hasattr(m, "predict")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(4, 20, 158), torch.zeros(4, 1))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m.prediction(torch.zeros(4, 20, 158))
+    with pytest.raises(NotImplementedError):
+        fb.FeatureExtractor(158, 20, num_layers=2)
+
+
+def test_oracle_is_not_imported_by_the_product():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import factorvae_b200, factorvae_b200.engine, factorvae_b200.module;"
+            "bad=[m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; assert not bad, bad") % ROOT
+    subprocess.run([sys.executable, "-c", code], check=True)
+    pkg = os.path.join(ROOT, "factorvae_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -63,3 +63,28 @@ def test_clamp_case_really_trips():
     g = load_golden("sigma_zero_clamp")
     assert float(g["out"]["sigma_post"][:, 1].max()) == pytest.approx(1e-6)
     assert float(g["out"]["sigma_prior"].max()) == pytest.approx(1e-6)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if n not in ("guard_inf_query",)])
+def test_cpu_port_matches_reference(name):
+    """oracle/cpu_port.py (the timed CPU baseline) reproduces the reference's loss and gradients."""
+    from oracle.cpu_port import CpuPort
+    g = load_golden(name)
+    xs, ys, epss, masks = split_by_date(g)
+    port = CpuPort(g["params"])
+    B = len(xs)
+    total, gsum = 0.0, {k: torch.zeros_like(v) for k, v in port.p.items()}
+    for d in range(B):
+        port.zero_grad()
+        loss, yhat, mu_y, sg_y = port.step_forward(xs[d], ys[d], train=g["dims"]["train"], eps=epss[d],
+                                                    keep_mask=None if masks is None else masks[d].float())
+        loss.backward()
+        total += float(loss) / B
+        for k, v in port.p.items():
+            if v.grad is not None:
+                gsum[k] += v.grad / B
+    assert abs(total - float(g["out"]["loss"])) <= 1e-5 * abs(float(g["out"]["loss"]))
+    gmax = max(float(v.abs().max()) for v in g["grads"].values())
+    for k, gr in g["grads"].items():
+        err = float((gsum[k] - gr).norm())
+        assert err <= 1e-4 * float(gr.norm()) + 2e-6 * gmax * gr.numel() ** 0.5, k

@@ -1,0 +1,214 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors written by the live
+reference and against the oracle restatement on fresh seeded inputs.
+
+Tolerances:
+  fp32 kernels : ELBO rel <= 1e-5, mu_y abs <= 1e-5, sigma_y rel <= 1e-5, grads rel-L2 <= 1e-4
+  bf16 tensor-core FeatureExtractor: ELBO rel <= 2e-2, mu_y abs <= 1e-2, sigma_y rel <= 2e-2,
+                                     grad cosine >= 0.999 and rel-L2 <= 3e-2
+"""
+import pytest
+import torch
+
+from conftest import golden_cases, load_golden, split_by_date
+
+pytestmark = pytest.mark.gpu
+
+
+def _relmax(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float(((a - b).abs() / b.abs().clamp_min(1e-30)).max())
+
+
+def _rel_l2(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _run_case(g, precision, dev, bf16_panel=False):
+    from factorvae_b200 import engine
+    d = g["dims"]
+    L = engine.ParamLayout(d["C"], d["H"], d["K"], d["M"])
+    flat = L.pack(g["params"], dev)
+    x = g["inp"]["x"].to(dev)
+    if bf16_panel:
+        x = x.to(torch.bfloat16)
+    y = g["inp"]["y"].to(dev)
+    eps = g["inp"]["eps"].to(dev)
+    km = g["inp"]["keep_mask"].t().contiguous().to(dev) if "keep_mask" in g["inp"] else None
+    out, st = engine.elbo_forward(L, flat, x, y, g["inp"]["date_ptr"].to(dev), eps=eps, keep_mask=km, train=d["train"],
+                                  precision=precision)
+    grad = engine.elbo_backward(L, st)
+    torch.cuda.synchronize()
+    return L, out, grad, st
+
+
+def _check_grads(L, grad, ref_grads, rtol, atol_scale):
+    gmax = max(float(v.abs().max()) for v in ref_grads.values())
+    worst = 0.0
+    for k, gr in ref_grads.items():
+        ours = L.view(grad, k).double().cpu()
+        err = float((ours - gr.double()).norm())
+        tol = rtol * float(gr.double().norm()) + atol_scale * gmax * (gr.numel() ** 0.5)
+        assert err <= tol, (k, err, tol)
+        worst = max(worst, err / (float(gr.double().norm()) + 1e-30))
+    return worst
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_fp32_kernels_match_reference_golden(name, cuda_device):
+    g = load_golden(name)
+    L, out, grad, st = _run_case(g, "fp32", cuda_device)
+    ref = g["out"]
+    loss, rl = float(out["loss"]), float(ref["loss"])
+    assert abs(loss - rl) <= 1e-5 * abs(rl), (loss, rl)
+    assert _rel_l2(out["date_loss"], ref["date_loss"]) <= 1e-5
+    assert float((out["mu_y"].cpu() - ref["mu_y"]).abs().max()) <= 1e-5 * max(1.0, float(ref["mu_y"].abs().max()))
+    assert _relmax(out["sigma_y"], ref["sigma_y"]) <= 1e-5
+    assert _rel_l2(out["yhat"], ref["yhat"]) <= 1e-5
+    for k in ("mu_post", "sigma_post", "mu_prior", "sigma_prior"):
+        assert _rel_l2(out[k], ref[k]) <= 1e-5, k
+    from factorvae_b200 import engine
+    assert _rel_l2(engine.latent(st), ref["e"]) <= 1e-5
+    # whole-gradient rel-L2 <= 1e-4, per tensor with an absolute floor for the round-off-only ones
+    allg = torch.cat([L.view(grad, k).reshape(-1).double().cpu() for k in g["grads"]])
+    allr = torch.cat([v.reshape(-1).double() for v in g["grads"].values()])
+    assert float((allg - allr).norm() / allr.norm()) <= 1e-4
+    _check_grads(L, grad, g["grads"], 1e-4, 2e-6)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_prediction_matches_reference_golden(name, cuda_device):
+    from factorvae_b200 import engine
+    g = load_golden(name)
+    d = g["dims"]
+    L = engine.ParamLayout(d["C"], d["H"], d["K"], d["M"])
+    flat = L.pack(g["params"], cuda_device)
+    out, _ = engine.elbo_forward(L, flat, g["inp"]["x"].to(cuda_device), None, g["inp"]["date_ptr"].to(cuda_device),
+                                 eps=g["inp"]["eps"].to(cuda_device), train=False, precision="fp32", predict=True)
+    assert _rel_l2(out["yhat"], g["pred"]["yhat"]) <= 1e-5
+    assert _rel_l2(out["mu_y"], g["pred"]["mu_y"]) <= 1e-5
+    assert _relmax(out["sigma_y"], g["pred"]["sigma_y"]) <= 1e-5
+
+
+def test_noncontiguous_pitch159_and_bf16_panel(cuda_device):
+    """train_model.py:18 feeds char_with_label[:, :, :-1] -- a view with row pitch 159."""
+    from factorvae_b200 import engine
+    g = load_golden("train_ragged")
+    d = g["dims"]
+    L = engine.ParamLayout(d["C"], d["H"], d["K"], d["M"])
+    flat = L.pack(g["params"], cuda_device)
+    x = g["inp"]["x"].to(cuda_device)
+    wide = torch.zeros(x.shape[0], x.shape[1], 159, device=cuda_device)
+    wide[:, :, :158] = x
+    wide[:, :, 158] = 7.0
+    xv = wide[:, :, :-1]
+    assert not xv.is_contiguous()
+    kw = dict(eps=g["inp"]["eps"].to(cuda_device), keep_mask=g["inp"]["keep_mask"].t().contiguous().to(cuda_device),
+              train=True, precision="fp32")
+    o1, _ = engine.elbo_forward(L, flat, x, g["inp"]["y"].to(cuda_device), g["inp"]["date_ptr"].to(cuda_device), **kw)
+    o2, _ = engine.elbo_forward(L, flat, xv, g["inp"]["y"].to(cuda_device), g["inp"]["date_ptr"].to(cuda_device), **kw)
+    assert torch.equal(o1["loss"], o2["loss"]) and torch.equal(o1["yhat"], o2["yhat"])
+    # bf16 panel, fp32 arithmetic: equals the fp32 run on the bf16-rounded panel
+    xb = x.to(torch.bfloat16)
+    o3, _ = engine.elbo_forward(L, flat, xb, g["inp"]["y"].to(cuda_device), g["inp"]["date_ptr"].to(cuda_device), **kw)
+    o4, _ = engine.elbo_forward(L, flat, xb.float(), g["inp"]["y"].to(cuda_device), g["inp"]["date_ptr"].to(cuda_device), **kw)
+    assert torch.equal(o3["loss"], o4["loss"])
+
+
+@pytest.mark.parametrize("shape", [dict(B=3, N=70, T=6, H=20, K=20, M=128), dict(B=2, N=130, T=3, H=48, K=48, M=128),
+                                   dict(B=2, N=65, T=4, H=60, K=60, M=128), dict(B=1, N=33, T=2, H=64, K=96, M=128)])
+def test_fp32_kernels_match_oracle_on_fresh_inputs(shape, cuda_device):
+    """Seeded synthetic dates at sizes the oracle finishes in seconds; covers the config (H, K) pairs."""
+    from factorvae_b200 import engine
+    from factorvae_b200 import module as fm
+    from oracle import restatement as R
+    B, N, T, H, K, M = (shape[k] for k in "BNTHKM")
+    torch.manual_seed(100 + H)
+    model = fm.FactorVAE(fm.FeatureExtractor(158, H), fm.FactorEncoder(K, M, H),
+                         fm.FactorDecoder(fm.AlphaLayer(H), fm.BetaLayer(H, K)), fm.FactorPredictor(H, K))
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(7)
+    ns = [N - 3 * d for d in range(B)]
+    xs = [torch.randn(n, T, 158, generator=g).clamp_(-3, 3) for n in ns]
+    ys = [torch.randn(n, generator=g) for n in ns]
+    epss = [torch.randn(n, generator=g) for n in ns]
+    masks = [(torch.rand(K, n, generator=g) >= 0.1) for n in ns]
+    ref, rgrads = R.elbo_step(params, xs, ys, epss, [m.float() for m in masks], need_grad=True, dtype=torch.float64)
+    L = engine.ParamLayout(158, H, K, M)
+    flat = L.pack(params, cuda_device)
+    date_ptr = torch.tensor([0] + list(torch.tensor(ns).cumsum(0)), dtype=torch.int32)
+    out, st = engine.elbo_forward(L, flat, torch.cat(xs).to(cuda_device), torch.cat(ys).to(cuda_device),
+                                  date_ptr.to(cuda_device), eps=torch.cat(epss).to(cuda_device),
+                                  keep_mask=torch.cat(masks, dim=1).t().contiguous().to(torch.uint8).to(cuda_device),
+                                  train=True, precision="fp32")
+    grad = engine.elbo_backward(L, st)
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    assert float((out["mu_y"].cpu().double() - ref["mu_y"]).abs().max()) <= 1e-5 * max(1.0, float(ref["mu_y"].abs().max()))
+    assert _relmax(out["sigma_y"], ref["sigma_y"]) <= 1e-5
+    allg = torch.cat([L.view(grad, k).reshape(-1).double().cpu() for k in rgrads])
+    allr = torch.cat([v.reshape(-1) for v in rgrads.values()])
+    assert float((allg - allr).norm() / allr.norm()) <= 1e-4
+    _check_grads(L, grad, rgrads, 1e-4, 2e-6)
+
+
+def test_module_dropin_forward_backward(cuda_device):
+    """The nn.Module boundary: load reference weights, inject the fixture's noise, compare loss + grads."""
+    import factorvae_b200 as fb
+    g = load_golden("cfg1_shape")
+    d = g["dims"]
+    fb.set_default_precision("fp32")
+    m = fb.FactorVAE(fb.FeatureExtractor(d["C"], d["H"]), fb.FactorEncoder(d["K"], d["M"], d["H"]),
+                     fb.FactorDecoder(fb.AlphaLayer(d["H"]), fb.BetaLayer(d["H"], d["K"])), fb.FactorPredictor(d["H"], d["K"]))
+    m.load_state_dict(g["params"])
+    m.to(cuda_device).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    x, y = g["inp"]["x"].to(cuda_device), g["inp"]["y"].reshape(-1, 1).to(cuda_device)
+    with fb.inject_noise(g["inp"]["eps"].to(cuda_device), g["inp"]["keep_mask"].t().contiguous().to(cuda_device)):
+        opt.zero_grad()
+        loss, rec, mu_post, sigma_post, mu_prior, sigma_prior = m(x, y)
+        assert rec.shape == (x.shape[0], 1) and mu_post.shape == (d["K"],) and sigma_prior.shape == (d["K"],)
+        lv = loss.item()
+        loss.backward()
+    assert abs(lv - float(g["out"]["loss"])) <= 1e-5 * abs(float(g["out"]["loss"]))
+    for k, p in m.named_parameters():
+        gr = g["grads"][k]
+        assert p.grad is not None and p.grad.shape == gr.shape
+    allg = torch.cat([p.grad.reshape(-1).double().cpu() for _, p in m.named_parameters()])
+    allr = torch.cat([g["grads"][k].reshape(-1).double() for k, _ in m.named_parameters()])
+    assert float((allg - allr).norm() / allr.norm()) <= 1e-4
+    before = m.factor_encoder.linear.weight.detach().clone()
+    opt.step()                                    # parameters are views of the flat buffer: Adam updates it in place
+    assert not torch.equal(before, m.factor_encoder.linear.weight.detach())
+    assert m.factor_encoder.linear.weight.data_ptr() == m._flat.data_ptr() + 4 * m._layout.slices["factor_encoder.linear.weight"][0]
+    sd = m.state_dict()
+    assert set(sd) == set(g["params"])
+    m.eval()
+    with torch.no_grad():
+        yp = m.prediction(x)
+    assert yp.shape == (x.shape[0], 1) and torch.isfinite(yp).all()
+    fb.set_default_precision("auto")
+
+
+def test_philox_noise_is_shard_invariant_and_sane(cuda_device):
+    """In-kernel RNG: the same (seed, step, unit) gives the same eps wherever the date is processed."""
+    from factorvae_b200 import engine
+    g = load_golden("train_ragged")
+    d = g["dims"]
+    L = engine.ParamLayout(d["C"], d["H"], d["K"], d["M"])
+    flat = L.pack(g["params"], cuda_device)
+    x, y, ptr = g["inp"]["x"].to(cuda_device), g["inp"]["y"].to(cuda_device), g["inp"]["date_ptr"]
+    full, _ = engine.elbo_forward(L, flat, x, y, ptr.to(cuda_device), train=True, precision="fp32", philox=(42, 3, 0))
+    a, b = int(ptr[1]), int(ptr[2])
+    part, _ = engine.elbo_forward(L, flat, x[a:b], y[a:b], torch.tensor([0, b - a], dtype=torch.int32, device=cuda_device),
+                                  train=True, precision="fp32", philox=(42, 3, a))
+    assert torch.allclose(full["yhat"][a:b], part["yhat"], rtol=0, atol=0)
+    assert torch.equal(full["date_loss"][1], part["date_loss"][0])
+    other, _ = engine.elbo_forward(L, flat, x, y, ptr.to(cuda_device), train=True, precision="fp32", philox=(42, 4, 0))
+    assert not torch.equal(full["yhat"], other["yhat"])
+    # eps = (yhat - mu_y) / sigma_y should look standard normal over a few thousand draws
+    big = torch.randn(4096, 2, d["C"], device=cuda_device)
+    o, _ = engine.elbo_forward(L, flat, big, torch.zeros(4096, device=cuda_device),
+                               torch.tensor([0, 4096], dtype=torch.int32, device=cuda_device), train=False,
+                               precision="fp32", philox=(1, 1, 0))
+    z = (o["yhat"] - o["mu_y"]) / o["sigma_y"]
+    assert abs(float(z.mean())) < 0.08 and abs(float(z.std()) - 1.0) < 0.08
