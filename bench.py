@@ -59,10 +59,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self._stop = gpu_index, [], threading.Event()
+        self.gpu_index, self.rows, self._halt = gpu_index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 r = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5)
@@ -70,10 +70,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]

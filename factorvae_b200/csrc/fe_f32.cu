@@ -346,6 +346,21 @@ void run_ln(const fvae_panel& x, const FeDims& d, int64_t row0, int nrows, const
 
 int64_t fe_f32_workspace_bytes(const FeDims& d) { return carve_f32(d, nullptr).bytes; }
 
+// shared with fe_tc.cu while its recurrence / backward still run the fp32 kernels
+struct FeF32Views { float *gi, *hall; };
+FeF32Views fe_f32_views(const FeDims& d, void* ws) {
+    WsF32 W = carve_f32(d, ws);
+    return FeF32Views{W.gi, W.hall};
+}
+int fe_f32_gru_forward(const FeDims& d, const FeW& w, void* ws, float* e, cudaStream_t st) {
+    WsF32 W = carve_f32(d, ws);
+    const size_t smem = (size_t(3) * d.H * d.H + 2 * GSEQ * 64) * sizeof(float);
+    cudaError_t ce = cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (ce != cudaSuccess) return int(ce);
+    gru_fwd_kernel<<<grid_rows(d.S, GSEQ), dim3(64, GSEQ), smem, st>>>(W.gi, w.Whh, w.bhh, d.S, d.T, d.H, W.hall, e); count_launch();
+    return int(cudaGetLastError());
+}
+
 int fe_f32_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, void* ws, cudaStream_t st) {
     WsF32 W = carve_f32(d, ws);
     const int64_t R = int64_t(d.S) * d.T;

@@ -1,0 +1,137 @@
+// Minimal hand-written sm_100a tensor-core layer: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM),
+// TMEM alloc / ld, mbarrier, proxy fences, UMMA shared-memory / instruction descriptors.
+//
+// Shared-memory operand layout used everywhere in this repo ("chunk-major", SWIZZLE_NONE):
+//     a tile of R rows x KC*8 bf16 is stored as  tile[chunk c][row r][8 elements]   (16 B per (c,r))
+//     byte offset(r, k) = (k/8) * (R*16) + r*16 + (k%8)*2
+// Read as a K-major operand (rows = M or N index, k = reduction index):
+//     core matrix = 8 rows x 16 B, contiguous 128 B;  SBO (8-row group stride) = 128 B;
+//     LBO (stride between the two 8-element k chunks of one K=16 MMA) = R*16 B.
+// Read as an MN-major operand (the 8-element chunks run along M/N, rows = reduction index):
+//     SBO (stride between 8-element MN chunks) = R*16 B;  LBO (stride between 8-row k groups) = 128 B.
+// So one tile serves both the row GEMMs (K-major) and the weight-gradient GEMMs (MN-major).
+// Descriptor bit layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor"
+// tables (same fields as CUTLASS cute/arch/mma_sm100_desc.hpp).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace fvae {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// ---- fences ---------------------------------------------------------------------------------------
+// generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one warp, power-of-two columns >= 32) ----------------------------------------
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+    static_assert(kCols == 32 || kCols == 64 || kCols == 128 || kCols == 256 || kCols == 512, "TMEM columns");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr >> 4) & 0x3FFF);            // [0,14)  start address >> 4
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;  // [16,30) leading-dimension byte offset >> 4
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;  // [32,46) stride-dimension byte offset >> 4
+    d |= uint64_t(1) << 46;                          // [46,48) descriptor version = 1
+    return d;                                        // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+// instruction descriptor for kind::f16: A,B = bf16, D = fp32
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4)                       // c_format = F32
+         | (1u << 7)                       // a_format = BF16
+         | (1u << 10)                      // b_format = BF16
+         | (uint32_t(a_mn_major) << 15)    // a_major: 0 = K-major, 1 = MN-major
+         | (uint32_t(b_mn_major) << 16)    // b_major
+         | ((N >> 3) << 17)                // n_dim
+         | ((M >> 4) << 24);               // m_dim
+}
+
+// ---- MMA issue (one thread): D[tmem] (+)= A[smem] * B[smem]^T -----------------------------------------
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: warp w reads lanes 32*(w%4)..+31, thread = one lane (row), 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// issue only (no wait): pair with tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// TMEM address: bits [31:16] lane, [15:0] column
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, uint32_t lane, uint32_t col) { return base + (lane << 16) + col; }
+
+// ---- packing helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// byte offset of (row, 8-element chunk) in a chunk-major tile of R rows
+__device__ __forceinline__ uint32_t tile_off(uint32_t R, uint32_t row, uint32_t chunk) { return chunk * (R * 16u) + row * 16u; }
+
+}  // namespace tc
+}  // namespace fvae
