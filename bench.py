@@ -93,9 +93,7 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     import torch
-    from oracle.cpu_port import CpuPort
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    from oracle.cpu_port import CpuPort, pick_threads
     params = build_params(wl["H"], wl["K"], wl["M"])
     port = CpuPort(params)
     g = torch.Generator().manual_seed(1234)
@@ -103,6 +101,7 @@ def run_reference(args, wl, rank, world):
     dates_per_step = 4
     xs = [torch.randn(wl["N"], wl["T"], C_FEATURES, generator=g).clamp_(-3, 3) for _ in range(dates_per_step)]
     ys = [torch.randn(wl["N"], 1, generator=g) for _ in range(dates_per_step)]
+    cores = pick_threads(port, xs[0], ys[0])      # fastest intra-op width on this host (of %d cpus)
     for _ in range(args.warmup):
         for x, y in zip(xs, ys):
             port.train_step(x, y)
@@ -114,7 +113,7 @@ def run_reference(args, wl, rank, world):
     units = args.steps * dates_per_step * wl["N"]
     value = units / dt
     sample = (f"{dates_per_step} dates/step of the workload's per-date shape (N={wl['N']},T={wl['T']},K=H={wl['K']}), one date per "
-              f"reference step (zero_grad, forward, loss.item(), backward; no optimizer), fp32 torch CPU, {cores} threads")
+              f"reference step (zero_grad, forward, loss.item(), backward; no optimizer), fp32 torch CPU, {cores} threads (fastest of 1..{os.cpu_count()} probed)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "date*stocks/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -1,287 +1,900 @@
-// FeatureExtractor, FVAE_PREC_BF16_TC: bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM.
+// FeatureExtractor, FVAE_PREC_BF16_TC: the whole FeatureExtractor forward + backward on tcgen05 tensor
+// cores (bf16 operands, fp32 accumulation in TMEM), sm_100a.  Restates reference module.py:22-31 and its
+// autograd (train_model.py:29); the fp32 CUDA-core restatement in fe_f32.cu is the GPU-side cross-check.
 //
-// Restates reference module.py:26-28 + the GRU input projection of :30 as ONE kernel per 128-row tile
-// (a row = one (stock, time) pair of the panel):
-//     x rows --LayerNorm(fp32)--> bf16 A tile --tcgen05.mma--> TMEM [128 x 160] (xn . W1^T)
-//            --epilogue: +b1, LeakyReLU, bf16--> A tile 2 --tcgen05.mma--> TMEM [128 x pad16(3H)] (u . W_ih^T)
-//            --epilogue: +b_ih--> gi[row][3H]
-// so the panel is read once and neither xn nor u ever touch HBM.  Operand tiles use the chunk-major
-// SWIZZLE_NONE layout of tc_sm100.cuh; weights are converted once per step into bf16 operand images.
+// Work unit: an ITEM = (sequence tile st of 128 stocks, time step t) = 128 rows of the panel = one UMMA M.
 //
-// The GRU recurrence and the backward chain currently reuse the fp32 kernels of fe_f32.cu on the same
-// workspace (gi / hall / dgh in fp32); they are being moved to tcgen05 tile by tile.
+//   K1 front_fwd  per item : x rows -> LayerNorm (fp32) -> xhat bf16 tile -> MMA [128x160]=(xhat . W1g^T)
+//                            -> +b1f, LeakyReLU, bf16 tile -> MMA [128xNC]=(u . W_ih^T) -> + bias -> GI tile
+//                            (LayerNorm's affine is folded into the weights: W1g = W1 diag(gamma),
+//                             b1f = b1 + W1 beta; the gate columns are permuted into blocks of 8 units
+//                             [r8|z8|n8] so one hidden unit's three gates sit in adjacent 16-byte chunks)
+//   K2 gru_fwd    per tile : for t: MMA [128xNC] = (h_{t-1} . W_hh^T) -> gates (fp32) -> h_t (fp32 regs,
+//                            bf16 operand tile in smem, bf16 HALL tile in HBM for backward)
+//   K3 gru_bwd    per tile : BPTT; per step MMA gh (recompute), gate gradients (fp32) -> dGI tile (in place)
+//                            and dgh tile, MMA dh += dgh . W_hh, MMA dW_hh += dgh^T . [h_{t-1} | 1] (TMEM
+//                            accumulators live across all tiles of the CTA; one flush per CTA)
+//   K4a front_bwd_w1 / K4b front_bwd_wih per item: recompute xhat, pre (MMA); du = dGI . W_ih (MMA);
+//                            dpre = du * LeakyReLU'; Q += dpre^T . [xhat | 1]; dWih += dGI^T . [u | 1]
+//                            (weight-gradient MMAs read the SAME smem tiles as MN-major operands)
+//   K5 post                : dW1 = Q diag(gamma) + db1 beta^T, dgamma = sum_o W1 .* Q, dbeta = W1^T db1,
+//                            un-permute dW_ih / db_ih.   (x is data: no LayerNorm input gradient, so the
+//                            dxn = dpre . W1 contraction of the reference's autograd is never computed)
+//
+// All operand tiles use the chunk-major SWIZZLE_NONE layout of tc_sm100.cuh.
 #include "fe.cuh"
 #include "tc_sm100.cuh"
 
 namespace fvae {
-
-// shared with fe_f32.cu
-struct FeF32Views { float *gi, *hall; };
-FeF32Views fe_f32_views(const FeDims& d, void* ws);
-int fe_f32_gru_forward(const FeDims& d, const FeW& w, void* ws, float* e, cudaStream_t st);
-
 namespace {
 
 using namespace tc;
 
-constexpr int CP = 160;          // C padded to a multiple of 16 (K of both GEMMs, N of GEMM 1)
+constexpr int CP = 160;          // C padded (K of the row GEMMs, N of GEMM 1); column C holds the constant 1
 constexpr int KCH = CP / 8;      // 20 chunks of 8 features
-constexpr int TM = 128;          // rows per tile = UMMA M
-constexpr uint32_t A_BYTES = KCH * TM * 16;      // 40960
-constexpr uint32_t W1_BYTES = KCH * CP * 16;     // 51200
-constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t ACC2_COL = 256;               // column of the second accumulator
+constexpr int TM = 128;          // rows per item = UMMA M = TMEM lanes
+constexpr uint32_t TILE_CH = TM * 16;            // bytes of one 8-column chunk of a 128-row tile (2048)
+constexpr uint32_t A_BYTES = KCH * TILE_CH;      // 40960: a [128 x 160] bf16 tile
+constexpr uint32_t W1_BYTES = KCH * CP * 16;     // 51200: a [160 x 160] bf16 image
 
-inline int pad16(int v) { return (v + 15) & ~15; }
+__host__ __device__ inline int pad16(int v) { return (v + 15) & ~15; }
+__host__ __device__ inline int nb8_of(int H) { return (H + 7) / 8; }
+__host__ __device__ inline int nc_of(int H) { return pad16(24 * nb8_of(H)); }     // gate columns (permuted, padded)
+__host__ __device__ inline int hp_of(int H) { return pad16(H + 1); }              // hidden columns + the ones column
+// gate g = gate*H + j  ->  column of the permuted layout
+__host__ __device__ inline int perm_col(int gate, int j) { return (j >> 3) * 24 + gate * 8 + (j & 7); }
+// column -> (gate, j); returns false for padding columns
+__host__ __device__ inline bool unperm_col(int col, int H, int& gate, int& j) {
+    const int blk = col / 24, rem = col % 24;
+    gate = rem >> 3;
+    j = blk * 8 + (rem & 7);
+    return blk < nb8_of(H) && j < H;
+}
 
-struct TcImages {      // bf16 operand images in global memory (chunk-major), rebuilt every step
-    __nv_bfloat16* w1;     // [KCH][CP rows n][8]     B of GEMM 1: W1[n][k]
-    __nv_bfloat16* wih;    // [KCH][N2 rows g][8]     B of GEMM 2: W_ih[g][k]
+// ---- workspace -----------------------------------------------------------------------------------
+struct TcWs {
+    __nv_bfloat16 *w1g, *wih, *wihT, *whh, *whhT;   // operand images
+    float *b1f, *bgi, *bhn;                         // [CP], [NC], [HP]
+    __nv_bfloat16 *gi;      // [NT][T][NC/8][128][8]   gate pre-activations, then (backward) their gradients
+    __nv_bfloat16 *hall;    // [NT][T][HP/8][128][8]   h_t operand tiles (column H = 1)
+    float *q;               // [2*128][CP]  Q = dpre^T [xhat|1]
+    float *dwih;            // [2*128][CP]  dGI^T [u|1]   (permuted rows)
     int64_t bytes;
 };
 
-TcImages carve_images(const FeDims& d, void* base) {
-    TcImages t;
+TcWs carve_tc(const FeDims& d, void* base) {
+    TcWs w;
     char* p = static_cast<char*>(base);
-    t.w1 = reinterpret_cast<__nv_bfloat16*>(p);  p += W1_BYTES;
-    t.wih = reinterpret_cast<__nv_bfloat16*>(p); p += size_t(KCH) * pad16(3 * d.H) * 16;
-    t.bytes = ((p - static_cast<char*>(base)) + 255) / 256 * 256;
-    return t;
+    auto take = [&](int64_t n) { char* r = p; p += (n + 255) / 256 * 256; return r; };
+    const int NC = nc_of(d.H), HP = hp_of(d.H);
+    const int64_t NT = (int64_t(d.S) + TM - 1) / TM;
+    w.w1g = reinterpret_cast<__nv_bfloat16*>(take(W1_BYTES));
+    w.wih = reinterpret_cast<__nv_bfloat16*>(take(int64_t(KCH) * NC * 16));
+    w.wihT = reinterpret_cast<__nv_bfloat16*>(take(int64_t(NC / 8) * CP * 16));
+    w.whh = reinterpret_cast<__nv_bfloat16*>(take(int64_t(HP / 8) * NC * 16));
+    w.whhT = reinterpret_cast<__nv_bfloat16*>(take(int64_t(NC / 8) * HP * 16));
+    w.b1f = reinterpret_cast<float*>(take(CP * 4));
+    w.bgi = reinterpret_cast<float*>(take(NC * 4));
+    w.bhn = reinterpret_cast<float*>(take(HP * 4));
+    w.gi = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(NC / 8) * TILE_CH));
+    w.hall = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(HP / 8) * TILE_CH));
+    w.q = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
+    w.dwih = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
+    w.bytes = p - static_cast<char*>(base);
+    return w;
 }
 
-// image[(k/8)][row][k%8] = W[row][k] (row-major fp32, ld = ldw), zero padded
-__global__ void make_kmajor_image_kernel(const float* __restrict__ W, int rows, int cols, int ldw, int rows_pad, int kchunks,
-                                         __nv_bfloat16* __restrict__ img) {
-    const int total = kchunks * rows_pad * 8;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int e = idx & 7, row = (idx >> 3) % rows_pad, c = (idx >> 3) / rows_pad;
-        const int k = c * 8 + e;
-        const float v = (row < rows && k < cols) ? W[size_t(row) * ldw + k] : 0.f;
-        img[idx] = __float2bfloat16(v);
-    }
-}
-
-struct FrontArgs {
-    const void* x; int x_bf16; int64_t seq_pitch, row_pitch; int contiguous;
-    int T, C, H, N2; int64_t R;
-    const float *ln_w, *ln_b, *b1, *bih;
-    const __nv_bfloat16 *w1img, *wihimg;
-    float* gi;     // [R][3H]
+// ---- K0: operand images (once per step; weights change every step) ------------------------------------
+struct PrepArgs {
+    int C, H, NC, HP;
+    const float *ln_w, *ln_b, *W1, *b1, *Wih, *Whh, *bih, *bhh;
+    TcWs ws;
 };
 
-template <typename XT>
-__device__ __forceinline__ float ld_stage(const unsigned char* row, int c) { return float(reinterpret_cast<const XT*>(row)[c]); }
+__device__ __forceinline__ void put_img(__nv_bfloat16* img, int rows, int row, int k, float v) {
+    img[(size_t(k >> 3) * rows + row) * 8 + (k & 7)] = __float2bfloat16(v);
+}
 
-// One CTA = 128 threads = 128 tile rows = 128 TMEM lanes.  Persistent over tiles.
+__global__ void tc_prep_kernel(PrepArgs a) {
+    const int C = a.C, H = a.H, NC = a.NC, HP = a.HP;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // W1g[n][k] = W1[n][k] * gamma[k]
+    for (int idx = tid; idx < CP * CP; idx += nth) {
+        const int n = idx / CP, k = idx % CP;
+        put_img(a.ws.w1g, CP, n, k, (n < C && k < C) ? a.W1[n * C + k] * a.ln_w[k] : 0.f);
+    }
+    // W_ih (rows permuted) and its transpose
+    for (int idx = tid; idx < NC * CP; idx += nth) {
+        const int col = idx / CP, k = idx % CP;
+        int gate, j;
+        const bool ok = unperm_col(col, H, gate, j) && k < C;
+        const float v = ok ? a.Wih[(gate * H + j) * C + k] : 0.f;
+        put_img(a.ws.wih, NC, col, k, v);       // B[n=col][k]
+        put_img(a.ws.wihT, CP, k, col, v);      // B[n=k(feature)][k=col]
+    }
+    // W_hh (rows permuted) and its transpose
+    for (int idx = tid; idx < NC * HP; idx += nth) {
+        const int col = idx / HP, k = idx % HP;
+        int gate, j;
+        const bool ok = unperm_col(col, H, gate, j) && k < H;
+        const float v = ok ? a.Whh[(gate * H + j) * H + k] : 0.f;
+        put_img(a.ws.whh, NC, col, k, v);
+        put_img(a.ws.whhT, HP, k, col, v);
+    }
+    for (int n = tid; n < CP; n += nth) {
+        float v = 0.f;
+        if (n < C) {
+            v = a.b1[n];
+            for (int k = 0; k < C; ++k) v = fmaf(a.W1[n * C + k], a.ln_b[k], v);
+        }
+        a.ws.b1f[n] = v;
+    }
+    for (int col = tid; col < NC; col += nth) {
+        int gate, j;
+        float v = 0.f;
+        if (unperm_col(col, H, gate, j)) v = a.bih[gate * H + j] + (gate < 2 ? a.bhh[gate * H + j] : 0.f);
+        a.ws.bgi[col] = v;
+    }
+    for (int j = tid; j < HP; j += nth) a.ws.bhn[j] = j < H ? a.bhh[2 * H + j] : 0.f;
+}
+
+// ---- shared pieces of the item kernels -------------------------------------------------------------------
+struct ItemArgs {
+    const void* x; int64_t seq_pitch, row_pitch;
+    int S, T, C, H, NC, HP; int64_t NT;
+    TcWs ws;
+};
+
+// raw rows [r0, r0+nr) of item (st, t) -> stage[r - r0][C] (zero rows beyond S); one warp per row
 template <typename XT>
-__global__ void __launch_bounds__(TM, 1) fe_tc_front_fwd_kernel(FrontArgs a) {
+__device__ __forceinline__ void load_rows(const ItemArgs& a, int64_t st, int t, unsigned char* stage, int r0, int nr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, C = a.C;
+    const int row_bytes = C * int(sizeof(XT));
+    for (int rr = warp; rr < nr; rr += TM / 32) {
+        unsigned char* dst = stage + size_t(rr) * row_bytes;
+        const int64_t s = st * TM + r0 + rr;
+        if (s < a.S) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + s * a.seq_pitch + int64_t(t) * a.row_pitch);
+            if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0 && (row_bytes & 3) == 0) {
+                for (int w = lane; w < row_bytes / 4; w += 32) reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(src)[w];
+            } else {
+                for (int c = lane; c < C; c += 32) reinterpret_cast<XT*>(dst)[c] = reinterpret_cast<const XT*>(src)[c];
+            }
+        } else {
+            for (int c = lane; c < C; c += 32) reinterpret_cast<XT*>(dst)[c] = XT(0.f);
+        }
+    }
+}
+
+// LayerNorm statistics of one row (fp32, exactly C features) and xhat -> bf16 tile row `trow`; column C := 1
+template <typename XT>
+__device__ __forceinline__ void layernorm_to_tile(const XT* row, int C, unsigned char* tile, int trow) {
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += float(row[c]);
+    const float mean = sum / float(C);
+    float sq = 0.f;
+    for (int c = 0; c < C; ++c) { const float dlt = float(row[c]) - mean; sq = fmaf(dlt, dlt, sq); }
+    const float rstd = rsqrtf(sq / float(C) + kLnEps);
+#pragma unroll 1
+    for (int ch = 0; ch < KCH; ++ch) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+            v[e] = (c < C) ? (float(row[c]) - mean) * rstd : (c == C ? 1.f : 0.f);
+        }
+        *reinterpret_cast<uint4*>(tile + tile_off(TM, trow, ch)) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+
+// stage + normalise the 128 rows of an item.  bf16 panels: one pass of 128 rows; fp32 panels: two passes of
+// 64 rows, so the stage never exceeds one [128 x 160] bf16 tile (40,448 <= 40,960 bytes).
+template <typename XT>
+__device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t st, int t, unsigned char* stage, unsigned char* tile) {
+    constexpr int RPP = sizeof(XT) == 2 ? TM : TM / 2;
+    const int tid = threadIdx.x;
+    for (int r0 = 0; r0 < TM; r0 += RPP) {
+        if (r0 > 0) __syncthreads();
+        load_rows<XT>(a, st, t, stage, r0, RPP);
+        __syncthreads();
+        if (tid >= r0 && tid < r0 + RPP)
+            layernorm_to_tile<XT>(reinterpret_cast<const XT*>(stage) + size_t(tid - r0) * a.C, a.C, tile, tid);
+    }
+}
+
+__device__ __forceinline__ void copy_image(unsigned char* dst, const void* src, uint32_t bytes) {
+    for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
+// row GEMM: D[128 x N] (tmem column dcol) = A(K-major tile, 128 rows) . B(K-major image, brows rows)^T over k16 steps
+__device__ __forceinline__ void issue_row_gemm(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t b_addr, uint32_t brows,
+                                               uint32_t N, int k16) {
+    const uint32_t idesc = make_idesc_bf16(TM, N, false, false);
+    for (int ks = 0; ks < k16; ++ks) {
+        const uint64_t ad = make_smem_desc(a_addr + ks * 2 * TILE_CH, TILE_CH, 128);
+        const uint64_t bd = make_smem_desc(b_addr + ks * 2 * (brows * 16), brows * 16, 128);
+        mma_bf16_ss(tmem + dcol, ad, bd, idesc, ks > 0);
+    }
+}
+// weight-gradient GEMM: D[128 x N] (+)= A^T . B with A, B 128-row tiles read MN-major; A's M block starts at chunk a_chunk0
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t a_chunk0, uint32_t b_addr,
+                                            uint32_t N, bool accumulate) {
+    const uint32_t idesc = make_idesc_bf16(TM, N, true, true);
+    for (int ks = 0; ks < TM / 16; ++ks) {
+        const uint64_t ad = make_smem_desc(a_addr + a_chunk0 * TILE_CH + ks * 256, 128, TILE_CH);
+        const uint64_t bd = make_smem_desc(b_addr + ks * 256, 128, TILE_CH);
+        mma_bf16_ss(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+    }
+}
+
+// ---- K1: front forward ---------------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(TM, 1) tc_front_fwd_kernel(ItemArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int C = a.C, H3 = 3 * a.H, N2 = a.N2;
-    const uint32_t wih_bytes = uint32_t(KCH) * N2 * 16;
-    // carve: weights | A1 | stage | A2 | vectors | barriers   (stage may spill into A2 for fp32 panels)
+    const int C = a.C, NC = a.NC, NCH = NC / 8;
     unsigned char* sW1 = smem;
     unsigned char* sWih = sW1 + W1_BYTES;
-    unsigned char* sA1 = sWih + wih_bytes;
-    unsigned char* sStage = sA1 + A_BYTES;
-    const uint32_t stage_bytes = (TM * C * uint32_t(sizeof(XT)) + 127u) & ~127u;
-    unsigned char* sA2 = sStage + (sizeof(XT) == 2 ? stage_bytes : stage_bytes - A_BYTES);
-    float* sVec = reinterpret_cast<float*>(sA2 + A_BYTES);     // gamma[CP] beta[CP] b1[CP] bih[N2]
-    float* sGamma = sVec; float* sBeta = sVec + CP; float* sB1 = sVec + 2 * CP; float* sBih = sVec + 3 * CP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBih + N2);   // 2 mbarriers
+    unsigned char* sA1 = sWih + uint32_t(KCH) * NC * 16;
+    unsigned char* sA2 = sA1 + A_BYTES;          // raw-row stage first, then the u tile
+    unsigned char* sTail = sA2 + A_BYTES;
+    float* sB1 = reinterpret_cast<float*>(sTail);
+    float* sBgi = sB1 + CP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBgi + NC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
-    // ---- one-time setup: weights -> smem, vectors, barriers, TMEM
-    for (uint32_t i = tid; i < W1_BYTES / 16; i += TM) reinterpret_cast<uint4*>(sW1)[i] = reinterpret_cast<const uint4*>(a.w1img)[i];
-    for (uint32_t i = tid; i < wih_bytes / 16; i += TM) reinterpret_cast<uint4*>(sWih)[i] = reinterpret_cast<const uint4*>(a.wihimg)[i];
-    for (int i = tid; i < CP; i += TM) {
-        sGamma[i] = i < C ? a.ln_w[i] : 0.f;
-        sBeta[i] = i < C ? a.ln_b[i] : 0.f;
-        sB1[i] = i < C ? a.b1[i] : 0.f;
-    }
-    for (int i = tid; i < N2; i += TM) sBih[i] = i < H3 ? a.bih[i] : 0.f;
+    copy_image(sW1, a.ws.w1g, W1_BYTES);
+    copy_image(sWih, a.ws.wih, uint32_t(KCH) * NC * 16);
+    for (int i = tid; i < CP; i += TM) sB1[i] = a.ws.b1f[i];
+    for (int i = tid; i < NC; i += TM) sBgi[i] = a.ws.bgi[i];
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = uint32_t(warp) * 32u;
-    const uint32_t idesc1 = make_idesc_bf16(TM, CP, false, false);
-    const uint32_t idesc2 = make_idesc_bf16(TM, uint32_t(N2), false, false);
-    const int64_t ntiles = (a.R + TM - 1) / TM;
+    const int64_t nitems = a.NT * a.T;
     uint32_t phase = 0;
-
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, phase ^= 1) {
-        const int64_t row0 = tile * TM;
-        const int nrows = int((a.R - row0 < TM) ? a.R - row0 : TM);
-        // ---- (a) raw rows -> stage
-        if (a.contiguous && nrows == TM) {
-            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const XT*>(a.x) + row0 * C);
-            const uint32_t n16 = TM * C * uint32_t(sizeof(XT)) / 16;
-            for (uint32_t i = tid; i < n16; i += TM) reinterpret_cast<uint4*>(sStage)[i] = src[i];
-        } else {
-            for (int r = warp; r < TM; r += TM / 32) {
-                XT* dst = reinterpret_cast<XT*>(sStage) + size_t(r) * C;
-                if (r < nrows) {
-                    const int64_t row = row0 + r;
-                    const XT* src = static_cast<const XT*>(a.x) + (row / a.T) * a.seq_pitch + (row % a.T) * a.row_pitch;
-                    for (int c = tid & 31; c < C; c += 32) dst[c] = src[c];
-                } else {
-                    for (int c = tid & 31; c < C; c += 32) dst[c] = XT(0.f);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- (b) LayerNorm of my row (fp32 statistics over exactly C features) -> bf16 A1
-        {
-            const unsigned char* rowp = sStage + size_t(tid) * C * sizeof(XT);
-            float sum = 0.f;
-            for (int c = 0; c < C; ++c) sum += ld_stage<XT>(rowp, c);
-            const float mean = sum / float(C);
-            float sq = 0.f;
-            for (int c = 0; c < C; ++c) { const float dlt = ld_stage<XT>(rowp, c) - mean; sq = fmaf(dlt, dlt, sq); }
-            const float rstd = rsqrtf(sq / float(C) + kLnEps);
-#pragma unroll 1
-            for (int ch = 0; ch < KCH; ++ch) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int c = ch * 8 + e;
-                    v[e] = (c < C) ? fmaf((ld_stage<XT>(rowp, c) - mean) * rstd, sGamma[c], sBeta[c]) : 0.f;
-                }
-                uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                *reinterpret_cast<uint4*>(sA1 + tile_off(TM, tid, ch)) = pk;
-            }
-        }
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, phase ^= 1) {
+        const int64_t st = item / a.T;
+        const int t = int(item % a.T);
+        stage_and_normalize<XT>(a, st, t, sA2, sA1);
         fence_async_smem();
         tc_fence_before_sync();
         __syncthreads();
-        // ---- (c) GEMM 1: [128 x 160] = A1 . W1^T
         if (tid == 0) {
             tc_fence_after_sync();
-            const uint32_t a0 = smem_u32(sA1), b0 = smem_u32(sW1);
-#pragma unroll
-            for (int ks = 0; ks < CP / 16; ++ks) {
-                const uint64_t ad = make_smem_desc(a0 + ks * 2 * (TM * 16), TM * 16, 128);
-                const uint64_t bd = make_smem_desc(b0 + ks * 2 * (CP * 16), CP * 16, 128);
-                mma_bf16_ss(tmem, ad, bd, idesc1, ks > 0);
-            }
+            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);
             mma_commit(&bars[0]);
         }
         mbar_wait(&bars[0], phase);
         tc_fence_after_sync();
-        // ---- (d) epilogue 1: +b1, LeakyReLU, bf16 -> A2
+        // u = LeakyReLU(pre + b1f) -> bf16 tile (stage is dead: every thread finished its LayerNorm before the sync)
 #pragma unroll 1
         for (int j = 0; j < CP / 16; ++j) {
             float v[16];
             tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = lrelu(v[e] + sB1[j * 16 + e]);
-            uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-            *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j)) = p0;
-            *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j + 1)) = p1;
+            for (int e = 0; e < 16; ++e) {
+                const int n = j * 16 + e;
+                v[e] = (n == C) ? 1.f : lrelu(v[e] + sB1[n]);
+            }
+            *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j)) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j + 1)) =
+                make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
         }
         fence_async_smem();
         tc_fence_before_sync();
         __syncthreads();
-        // ---- (e) GEMM 2: [128 x N2] = A2 . W_ih^T
         if (tid == 0) {
             tc_fence_after_sync();
-            const uint32_t a0 = smem_u32(sA2), b0 = smem_u32(sWih);
-#pragma unroll
-            for (int ks = 0; ks < CP / 16; ++ks) {
-                const uint64_t ad = make_smem_desc(a0 + ks * 2 * (TM * 16), TM * 16, 128);
-                const uint64_t bd = make_smem_desc(b0 + ks * 2 * (uint32_t(N2) * 16), uint32_t(N2) * 16, 128);
-                mma_bf16_ss(tmem + ACC2_COL, ad, bd, idesc2, ks > 0);
-            }
+            issue_row_gemm(tmem, 256, smem_u32(sA2), smem_u32(sWih), NC, NC, KCH / 2);
             mma_commit(&bars[1]);
         }
         mbar_wait(&bars[1], phase);
         tc_fence_after_sync();
-        // ---- (f) epilogue 2: +b_ih -> gi
+        // gi = acc + (b_ih [+ b_hr, b_hz]) -> bf16 GI tile (coalesced 16-byte chunks)
         {
-            float* out = a.gi + (row0 + tid) * H3;
+            unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
 #pragma unroll 1
-            for (int j = 0; j < N2 / 16; ++j) {
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, ACC2_COL + j * 16), v);
-                if (tid < nrows) {
+            for (int ch = 0; ch < NCH; ++ch) {
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, 256 + ch * 8), v);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int n = j * 16 + e;
-                        if (n < H3) out[n] = v[e] + sBih[n];
+                for (int e = 0; e < 8; ++e) v[e] += sBgi[ch * 8 + e];
+                *reinterpret_cast<uint4*>(gout + tile_off(TM, tid, ch)) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---- K2: GRU forward -------------------------------------------------------------------------------------------
+struct GruArgs {
+    int S, T, H, NC, HP; int64_t NT;
+    TcWs ws;
+    float* e;             // [S][H]
+    const float* dE;      // [S][H]   (backward)
+    float *gWhh, *gbhh;   // gradient sections (backward)
+};
+
+template <int NB8, uint32_t TCOLS>
+__global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int H = a.H, NC = a.NC, HP = a.HP, NCH = NC / 8, HCH = HP / 8;
+    unsigned char* sWhh = smem;                                   // [HCH][NC][16]
+    unsigned char* sH = sWhh + uint32_t(HCH) * NC * 16;           // [HCH][128][16]
+    float* sBhn = reinterpret_cast<float*>(sH + uint32_t(HCH) * TILE_CH);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sBhn + HP);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    copy_image(sWhh, a.ws.whh, uint32_t(HCH) * NC * 16);
+    for (int i = tid; i < HP; i += TM) sBhn[i] = a.ws.bhn[i];
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp) * 32u;
+    uint32_t phase = 0;
+    for (int64_t st = blockIdx.x; st < a.NT; st += gridDim.x) {
+        float h[8 * NB8];
+#pragma unroll
+        for (int j = 0; j < 8 * NB8; ++j) h[j] = 0.f;
+        const int64_t s = st * TM + tid;
+        for (int t = 0; t < a.T; ++t) {
+            if (t > 0) {
+                fence_async_smem();
+                tc_fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    issue_row_gemm(tmem, 0, smem_u32(sH), smem_u32(sWhh), NC, NC, HP / 16);
+                    mma_commit(bar);
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1;
+                tc_fence_after_sync();
+            }
+            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
+            unsigned char* hout = reinterpret_cast<unsigned char*>(a.ws.hall) + size_t(st * a.T + t) * HCH * TILE_CH;
+#pragma unroll
+            for (int b = 0; b < NB8; ++b) {
+                float ghr[8], ghz[8], ghn[8], gir[8], giz[8], gin8[8];
+                if (t > 0) {
+                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24), ghr);
+                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 8), ghz);
+                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 16), ghn);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ghr[u] = ghz[u] = ghn[u] = 0.f;
+                }
+                unpack8(*reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, 3 * b)), gir);
+                unpack8(*reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, 3 * b + 1)), giz);
+                unpack8(*reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, 3 * b + 2)), gin8);
+                float hv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = b * 8 + u;
+                    const float r = sigmoid_fast(gir[u] + ghr[u]);
+                    const float z = sigmoid_fast(giz[u] + ghz[u]);
+                    const float n = tanh_fast(gin8[u] + r * (ghn[u] + sBhn[j]));
+                    float hn = fmaf(z, h[j] - n, n);            // (1-z) n + z h
+                    if (j >= H) hn = 0.f;
+                    h[j] = hn;
+                    hv[u] = (j == H) ? 1.f : hn;                 // the ones column of the operand tile
+                }
+                const uint4 pk = make_uint4(pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]), pack_bf16(hv[4], hv[5]), pack_bf16(hv[6], hv[7]));
+                *reinterpret_cast<uint4*>(sH + tile_off(TM, tid, b)) = pk;
+                *reinterpret_cast<uint4*>(hout + tile_off(TM, tid, b)) = pk;
+            }
+            for (int b = NB8; b < HCH; ++b) {                    // padding chunks (hold the ones column when H % 8 == 0)
+                const uint32_t one = (H >= b * 8 && H < b * 8 + 8) ? (0x3F80u << (16 * (H & 1))) : 0u;
+                uint4 pk = make_uint4(0, 0, 0, 0);
+                const int w = (H - b * 8) >> 1;
+                if (one) { if (w == 0) pk.x = one; else if (w == 1) pk.y = one; else if (w == 2) pk.z = one; else pk.w = one; }
+                *reinterpret_cast<uint4*>(sH + tile_off(TM, tid, b)) = pk;
+                *reinterpret_cast<uint4*>(hout + tile_off(TM, tid, b)) = pk;
+            }
+            tc_fence_before_sync();
+        }
+        if (s < a.S) {
+#pragma unroll
+            for (int j = 0; j < 8 * NB8; ++j) if (j < H) a.e[s * H + j] = h[j];
+        }
+        __syncthreads();      // sH is rewritten by the next tile's first step only after everyone is done
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TCOLS>(tmem);
+}
+
+// ---- K3: GRU backward (BPTT) -------------------------------------------------------------------------------------
+template <int NB8, uint32_t TCOLS>
+__global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int H = a.H, NC = a.NC, HP = a.HP, NCH = NC / 8, HCH = HP / 8;
+    const int MB = NC > 128 ? 2 : 1;                              // M blocks of the dW_hh accumulator
+    unsigned char* sWhh = smem;                                   // [HCH][NC][16]   B of gh = h W_hh^T
+    unsigned char* sWhhT = sWhh + uint32_t(HCH) * NC * 16;        // [NCH][HP][16]   B of dh += dgh W_hh
+    unsigned char* sHp = sWhhT + uint32_t(NCH) * HP * 16;         // [HCH][128][16]  h_{t-1} (column H = 1)
+    unsigned char* sDgh = sHp + uint32_t(HCH) * TILE_CH;          // [16*MB][128][16] dgh (only NCH chunks are written)
+    float* sBhn = reinterpret_cast<float*>(sDgh + uint32_t(16 * MB) * TILE_CH);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBhn + HP);      // 0: gh, 1: dh, 2: dW
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    const uint32_t COL_DH = uint32_t(NC), COL_DW = uint32_t(NC + HP);
+    copy_image(sWhh, a.ws.whh, uint32_t(HCH) * NC * 16);
+    copy_image(sWhhT, a.ws.whhT, uint32_t(NCH) * HP * 16);
+    for (uint32_t i = tid; i < uint32_t(16 * MB) * TILE_CH / 16; i += TM) reinterpret_cast<uint4*>(sDgh)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < HP; i += TM) sBhn[i] = a.ws.bhn[i];
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp) * 32u;
+    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+    bool dw_pending = false, dw_started = false;
+    for (int64_t st = blockIdx.x; st < a.NT; st += gridDim.x) {
+        float dh[8 * NB8];
+        const int64_t s = st * TM + tid;
+#pragma unroll
+        for (int j = 0; j < 8 * NB8; ++j) dh[j] = (s < a.S && j < H) ? a.dE[s * H + j] : 0.f;
+        for (int t = a.T - 1; t >= 0; --t) {
+            if (dw_pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; dw_pending = false; }   // sHp / sDgh are free again
+            // h_{t-1} operand tile
+            if (t > 0) {
+                const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 1) * HCH * TILE_CH;
+                for (int b = 0; b < HCH; ++b)
+                    *reinterpret_cast<uint4*>(sHp + tile_off(TM, tid, b)) = *reinterpret_cast<const uint4*>(hin + tile_off(TM, tid, b));
+            } else {
+                for (int b = 0; b < HCH; ++b) {
+                    uint4 pk = make_uint4(0, 0, 0, 0);
+                    if (H >= b * 8 && H < b * 8 + 8) {
+                        const uint32_t one = 0x3F80u << (16 * (H & 1));
+                        const int w = (H - b * 8) >> 1;
+                        if (w == 0) pk.x = one; else if (w == 1) pk.y = one; else if (w == 2) pk.z = one; else pk.w = one;
+                    }
+                    *reinterpret_cast<uint4*>(sHp + tile_off(TM, tid, b)) = pk;
+                }
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (t > 0) {
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    issue_row_gemm(tmem, 0, smem_u32(sHp), smem_u32(sWhh), NC, NC, HP / 16);
+                    mma_commit(&bars[0]);
+                }
+                mbar_wait(&bars[0], ph0);
+                ph0 ^= 1;
+                tc_fence_after_sync();
+            }
+            unsigned char* gio = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
+#pragma unroll
+            for (int b = 0; b < NB8; ++b) {
+                float ghr[8], ghz[8], ghn[8], gir[8], giz[8], gin8[8], hp[8];
+                if (t > 0) {
+                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24), ghr);
+                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 8), ghz);
+                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 16), ghn);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ghr[u] = ghz[u] = ghn[u] = 0.f;
+                }
+                unpack8(*reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, 3 * b)), gir);
+                unpack8(*reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, 3 * b + 1)), giz);
+                unpack8(*reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, 3 * b + 2)), gin8);
+                unpack8(*reinterpret_cast<const uint4*>(sHp + tile_off(TM, tid, b)), hp);
+                float dar[8], daz[8], dan[8], dnr[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = b * 8 + u;
+                    const float r = sigmoid_fast(gir[u] + ghr[u]);
+                    const float z = sigmoid_fast(giz[u] + ghz[u]);
+                    const float hn = ghn[u] + sBhn[j];
+                    const float n = tanh_fast(gin8[u] + r * hn);
+                    const float hprev = (j < H) ? hp[u] : 0.f;
+                    const float d = dh[j];
+                    const float dn = d * (1.f - z);
+                    const float dz = d * (hprev - n);
+                    dan[u] = dn * (1.f - n * n);
+                    dar[u] = dan[u] * hn * r * (1.f - r);
+                    daz[u] = dz * z * (1.f - z);
+                    dnr[u] = dan[u] * r;
+                    dh[j] = d * z;
+                }
+                const uint4 pr = make_uint4(pack_bf16(dar[0], dar[1]), pack_bf16(dar[2], dar[3]), pack_bf16(dar[4], dar[5]), pack_bf16(dar[6], dar[7]));
+                const uint4 pz = make_uint4(pack_bf16(daz[0], daz[1]), pack_bf16(daz[2], daz[3]), pack_bf16(daz[4], daz[5]), pack_bf16(daz[6], daz[7]));
+                const uint4 pn = make_uint4(pack_bf16(dan[0], dan[1]), pack_bf16(dan[2], dan[3]), pack_bf16(dan[4], dan[5]), pack_bf16(dan[6], dan[7]));
+                const uint4 pq = make_uint4(pack_bf16(dnr[0], dnr[1]), pack_bf16(dnr[2], dnr[3]), pack_bf16(dnr[4], dnr[5]), pack_bf16(dnr[6], dnr[7]));
+                *reinterpret_cast<uint4*>(gio + tile_off(TM, tid, 3 * b)) = pr;          // d gi, in place
+                *reinterpret_cast<uint4*>(gio + tile_off(TM, tid, 3 * b + 1)) = pz;
+                *reinterpret_cast<uint4*>(gio + tile_off(TM, tid, 3 * b + 2)) = pn;
+                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b)) = pr;         // d gh operand tile
+                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b + 1)) = pz;
+                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b + 2)) = pq;
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                issue_row_gemm(tmem, COL_DH, smem_u32(sDgh), smem_u32(sWhhT), HP, HP, NC / 16);       // dh part = dgh . W_hh
+                mma_commit(&bars[1]);
+                for (int mb = 0; mb < MB; ++mb)                                                          // dW_hh += dgh^T [h_{t-1} | 1]
+                    issue_wgrad(tmem, COL_DW + mb * HP, smem_u32(sDgh), 16 * mb, smem_u32(sHp), HP, dw_started);
+                mma_commit(&bars[2]);
+            }
+            dw_started = true;
+            dw_pending = true;
+            mbar_wait(&bars[1], ph1);
+            ph1 ^= 1;
+            tc_fence_after_sync();
+#pragma unroll
+            for (int b = 0; b < NB8; ++b) {
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_DH + b * 8), v);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dh[b * 8 + u] += v[u];
+            }
+            tc_fence_before_sync();
+        }
+    }
+    if (dw_pending) { mbar_wait(&bars[2], ph2); }
+    tc_fence_after_sync();
+    // flush dW_hh / db_hh: lane = permuted gate row, columns = hidden index (column H = bias)
+    if (dw_started) {
+        for (int mb = 0; mb < MB; ++mb) {
+            const int col = mb * 128 + tid;
+            int gate, j;
+            const bool ok = col < NC && unperm_col(col, H, gate, j);
+            for (int c8 = 0; c8 < HCH; ++c8) {
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_DW + mb * HP + c8 * 8), v);
+                if (ok) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = c8 * 8 + u;
+                        if (k < H) atomicAdd(a.gWhh + size_t(gate * H + j) * H + k, v[u]);
+                        else if (k == H) atomicAdd(a.gbhh + gate * H + j, v[u]);
                     }
                 }
             }
         }
-        tc_fence_before_sync();
-        __syncthreads();     // stage / A1 / TMEM may be overwritten by the next tile
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+    if (warp == 0) tmem_dealloc<TCOLS>(tmem);
 }
 
-size_t front_smem_bytes(int C, int N2, size_t esize) {
-    const size_t stage = (size_t(TM) * C * esize + 127) & ~size_t(127);
-    size_t b = W1_BYTES + size_t(KCH) * N2 * 16 + A_BYTES;
-    b += (esize == 2) ? stage + A_BYTES : stage;       // fp32 staging overlaps A2
-    b += (3 * CP + N2) * sizeof(float) + 2 * sizeof(uint64_t) + 16;
-    return b;
+// ---- K4: front backward (weight gradients) ----------------------------------------------------------------------------
+// MODE 0: Q    += dpre^T [xhat | 1]   (dpre = (dGI . W_ih) * LeakyReLU'(pre))
+// MODE 1: dWih += dGI^T  [u | 1]
+template <typename XT, int MODE>
+__global__ void __launch_bounds__(TM, 1) tc_front_bwd_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int C = a.C, NC = a.NC, NCH = NC / 8;
+    const int MBW = NC > 128 ? 2 : 1;
+    unsigned char* sW1 = smem;
+    unsigned char* sNext = sW1 + W1_BYTES;
+    unsigned char* sWihT = sNext;                                  // MODE 0 only: [NCH][CP][16]
+    if (MODE == 0) sNext += uint32_t(NCH) * CP * 16;
+    unsigned char* sA1 = sNext;  sNext += A_BYTES;                 // xhat tile
+    unsigned char* sA2 = sNext;                                    // MODE 1 only: u tile
+    if (MODE == 1) sNext += A_BYTES;
+    unsigned char* sScr = sNext;                                   // raw rows -> dGI tile -> dpre tile (32 chunks)
+    sNext += 32 * TILE_CH;
+    float* sB1 = reinterpret_cast<float*>(sNext);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + CP);        // 0: pre, 1: du, 2: wgrad
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    copy_image(sW1, a.ws.w1g, W1_BYTES);
+    if (MODE == 0) copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
+    for (int i = tid; i < CP; i += TM) sB1[i] = a.ws.b1f[i];
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp) * 32u;
+    const uint32_t COL_ACC = 160;          // wgrad accumulators: [160, 480)
+    const int64_t nitems = a.NT * a.T;
+    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+    bool pending = false, started = false;
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int64_t st = item / a.T;
+        const int t = int(item % a.T);
+        if (pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }       // tiles are free again
+        stage_and_normalize<XT>(a, st, t, sScr, sA1);
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);   // pre
+            mma_commit(&bars[0]);
+        }
+        // dGI tile of this item -> scratch (the raw rows are dead), overlapping the MMA
+        {
+            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
+            for (int ch = 0; ch < NCH; ++ch)
+                *reinterpret_cast<uint4*>(sScr + tile_off(TM, tid, ch)) = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, ch));
+        }
+        mbar_wait(&bars[0], ph0);
+        ph0 ^= 1;
+        tc_fence_after_sync();
+        if (MODE == 1) {
+            // u = LeakyReLU(pre + b1f) -> bf16 tile, column C := 1
+#pragma unroll 1
+            for (int j = 0; j < CP / 16; ++j) {
+                float v[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int n = j * 16 + e;
+                    v[e] = (n == C) ? 1.f : lrelu(v[e] + sB1[n]);
+                }
+                *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j)) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j + 1)) =
+                    make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                for (int mb = 0; mb < MBW; ++mb)
+                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA2), CP, started);
+                mma_commit(&bars[2]);
+            }
+        } else {
+            // LeakyReLU' mask of my row: 160 bits
+            uint32_t mask[CP / 32];
+#pragma unroll
+            for (int w = 0; w < CP / 32; ++w) mask[w] = 0u;
+#pragma unroll
+            for (int j = 0; j < CP / 16; ++j) {
+                float v[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int n = j * 16 + e;
+                    if (v[e] + sB1[n] > 0.f) mask[n >> 5] |= 1u << (n & 31);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                issue_row_gemm(tmem, 0, smem_u32(sScr), smem_u32(sWihT), CP, CP, NC / 16);     // du = dGI . W_ih
+                mma_commit(&bars[1]);
+            }
+            mbar_wait(&bars[1], ph1);
+            ph1 ^= 1;
+            tc_fence_after_sync();
+            // dpre = du * LeakyReLU'(pre) -> bf16 tile over the (dead) dGI tile
+#pragma unroll
+            for (int j = 0; j < CP / 16; ++j) {
+                float v[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int n = j * 16 + e;
+                    v[e] *= ((mask[n >> 5] >> (n & 31)) & 1u) ? 1.f : kLeakySlope;
+                }
+                *reinterpret_cast<uint4*>(sScr + tile_off(TM, tid, 2 * j)) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                *reinterpret_cast<uint4*>(sScr + tile_off(TM, tid, 2 * j + 1)) =
+                    make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                for (int mb = 0; mb < 2; ++mb)
+                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA1), CP, started);
+                mma_commit(&bars[2]);
+            }
+        }
+        started = true;
+        pending = true;
+    }
+    if (pending) mbar_wait(&bars[2], ph2);
+    tc_fence_after_sync();
+    if (started) {
+        float* outbuf = MODE == 0 ? a.ws.q : a.ws.dwih;
+        const int nblk = MODE == 0 ? 2 : MBW;
+        for (int mb = 0; mb < nblk; ++mb) {
+            const int row = mb * 128 + tid;
+            const bool ok = MODE == 0 ? row < C : row < NC;
+            for (int j = 0; j < CP / 16; ++j) {
+                float v[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + j * 16), v);
+                if (ok) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(outbuf + size_t(row) * CP + j * 16 + e, v[e]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
+// ---- K5: assemble the parameter gradients from Q / dWih ---------------------------------------------------------------------
+struct PostArgs {
+    int C, H, NC;
+    const float *ln_w, *ln_b, *W1;
+    const float *q, *dwih;
+    FeG g;
+};
+__global__ void tc_post_kernel(PostArgs a) {
+    const int C = a.C, H = a.H;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // dW1[o][i] = Q[o][i] gamma[i] + db1[o] beta[i];  db1[o] = Q[o][C]
+    for (int idx = tid; idx < C * C; idx += nth) {
+        const int o = idx / C, i = idx % C;
+        atomicAdd(a.g.W1 + idx, a.q[o * CP + i] * a.ln_w[i] + a.q[o * CP + C] * a.ln_b[i]);
+    }
+    for (int o = tid; o < C; o += nth) atomicAdd(a.g.b1 + o, a.q[o * CP + C]);
+    // dgamma[i] = sum_o W1[o][i] Q[o][i];  dbeta[i] = sum_o W1[o][i] db1[o]
+    for (int i = tid; i < C; i += nth) {
+        float dg = 0.f, db = 0.f;
+        for (int o = 0; o < C; ++o) {
+            const float w = a.W1[o * C + i];
+            dg = fmaf(w, a.q[o * CP + i], dg);
+            db = fmaf(w, a.q[o * CP + C], db);
+        }
+        atomicAdd(a.g.ln_w + i, dg);
+        atomicAdd(a.g.ln_b + i, db);
+    }
+    // dW_ih / db_ih: un-permute the gate rows
+    for (int idx = tid; idx < 3 * H * (C + 1); idx += nth) {
+        const int g = idx / (C + 1), i = idx % (C + 1);
+        const int col = perm_col(g / H, g % H);
+        const float v = a.dwih[size_t(col) * CP + (i < C ? i : C)];
+        if (i < C) atomicAdd(a.g.Wih + size_t(g) * C + i, v);
+        else atomicAdd(a.g.bih + g, v);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------------
+int num_sms() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+template <typename KernelT>
+int launch_smem(KernelT k, int grid, size_t smem, cudaStream_t st, const ItemArgs& a) {
+    if (smem > 227 * 1024) return FVAE_ERR_LIMIT;
+    cudaError_t ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (ce != cudaSuccess) return int(ce);
+    k<<<grid, TM, smem, st>>>(a); count_launch();
+    return int(cudaGetLastError());
+}
+template <typename KernelT>
+int launch_gru(KernelT k, int grid, size_t smem, cudaStream_t st, const GruArgs& a) {
+    if (smem > 227 * 1024) return FVAE_ERR_LIMIT;
+    cudaError_t ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (ce != cudaSuccess) return int(ce);
+    k<<<grid, TM, smem, st>>>(a); count_launch();
+    return int(cudaGetLastError());
+}
+
+ItemArgs make_item_args(const FeDims& d, const fvae_panel& x, const TcWs& ws) {
+    ItemArgs a;
+    a.x = x.data; a.seq_pitch = x.seq_pitch; a.row_pitch = x.row_pitch;
+    a.S = d.S; a.T = d.T; a.C = d.C; a.H = d.H; a.NC = nc_of(d.H); a.HP = hp_of(d.H);
+    a.NT = (int64_t(d.S) + TM - 1) / TM;
+    a.ws = ws;
+    return a;
+}
+
+#define FVAE_DISPATCH_NB8(NB, CALL)                                   \
+    switch (NB) {                                                     \
+        case 1: { constexpr int kNB = 1; CALL; } break;               \
+        case 2: { constexpr int kNB = 2; CALL; } break;               \
+        case 3: { constexpr int kNB = 3; CALL; } break;               \
+        case 4: { constexpr int kNB = 4; CALL; } break;               \
+        case 5: { constexpr int kNB = 5; CALL; } break;               \
+        case 6: { constexpr int kNB = 6; CALL; } break;               \
+        case 7: { constexpr int kNB = 7; CALL; } break;               \
+        default: { constexpr int kNB = 8; CALL; } break;              \
+    }
 
 }  // namespace
 
 int fe_tc_supported(const FeDims& d) {
-    if (d.C > CP || d.C < 16 || d.H > kMaxH) return FVAE_ERR_UNSUPPORTED;
+    if (d.C >= CP || d.C < 8 || d.H > kMaxH || d.H < 1) return FVAE_ERR_UNSUPPORTED;   // column C carries the constant 1
     return 0;
 }
 
-int64_t fe_tc_workspace_bytes(const FeDims& d) {
-    const int64_t f32 = (fe_f32_workspace_bytes(d) + 255) / 256 * 256;
-    return f32 + carve_images(d, nullptr).bytes;
-}
+int64_t fe_tc_workspace_bytes(const FeDims& d) { return carve_tc(d, nullptr).bytes; }
 
-int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, void* ws, cudaStream_t st) {
-    const int64_t f32 = (fe_f32_workspace_bytes(d) + 255) / 256 * 256;
-    TcImages img = carve_images(d, static_cast<char*>(ws) + f32);
-    FeF32Views v = fe_f32_views(d, ws);
-    const int N2 = pad16(3 * d.H);
-    make_kmajor_image_kernel<<<32, 256, 0, st>>>(w.W1, d.C, d.C, d.C, CP, KCH, img.w1); count_launch();
-    make_kmajor_image_kernel<<<32, 256, 0, st>>>(w.Wih, 3 * d.H, d.C, d.C, N2, KCH, img.wih); count_launch();
-    FrontArgs a;
-    a.x = x.data; a.x_bf16 = (x.dtype == FVAE_BF16); a.seq_pitch = x.seq_pitch; a.row_pitch = x.row_pitch;
-    a.contiguous = (x.row_pitch == d.C && x.seq_pitch == int64_t(d.T) * d.C && (reinterpret_cast<uintptr_t>(x.data) % 16 == 0));
-    a.T = d.T; a.C = d.C; a.H = d.H; a.N2 = N2; a.R = int64_t(d.S) * d.T;
-    a.ln_w = w.ln_w; a.ln_b = w.ln_b; a.b1 = w.b1; a.bih = w.bih;
-    a.w1img = img.w1; a.wihimg = img.wih; a.gi = v.gi;
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t ntiles = (a.R + TM - 1) / TM;
-    const int grid = int(ntiles < nsm ? ntiles : nsm);
-    cudaError_t ce;
-    if (a.x_bf16) {
-        const size_t smem = front_smem_bytes(d.C, N2, 2);
-        if (smem > 227 * 1024) return FVAE_ERR_LIMIT;
-        if ((ce = cudaFuncSetAttribute(fe_tc_front_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return int(ce);
-        fe_tc_front_fwd_kernel<__nv_bfloat16><<<grid, TM, smem, st>>>(a); count_launch();
-    } else {
-        const size_t smem = front_smem_bytes(d.C, N2, 4);
-        if (smem > 227 * 1024) return FVAE_ERR_LIMIT;
-        if ((ce = cudaFuncSetAttribute(fe_tc_front_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess) return int(ce);
-        fe_tc_front_fwd_kernel<float><<<grid, TM, smem, st>>>(a); count_launch();
+int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, void* wsp, cudaStream_t st) {
+    TcWs ws = carve_tc(d, wsp);
+    const int NC = nc_of(d.H), HP = hp_of(d.H), NB = nb8_of(d.H);
+    PrepArgs p{d.C, d.H, NC, HP, w.ln_w, w.ln_b, w.W1, w.b1, w.Wih, w.Whh, w.bih, w.bhh, ws};
+    tc_prep_kernel<<<64, 256, 0, st>>>(p); count_launch();
+    ItemArgs a = make_item_args(d, x, ws);
+    const int nsm = num_sms();
+    const int64_t nitems = a.NT * d.T;
+    int rc;
+    {
+        const int grid = int(nitems < nsm ? nitems : nsm);
+        const size_t smem = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + (CP + NC) * 4 + 64;
+        if (x.dtype == FVAE_BF16) rc = launch_smem(tc_front_fwd_kernel<__nv_bfloat16>, grid, smem, st, a);
+        else rc = launch_smem(tc_front_fwd_kernel<float>, grid, smem, st, a);
+        if (rc != 0) return rc;
     }
-    if ((ce = cudaGetLastError()) != cudaSuccess) return int(ce);
-    return fe_f32_gru_forward(d, w, ws, e, st);
+    GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, e, nullptr, nullptr, nullptr};
+    const size_t smem = size_t(HP / 8) * NC * 16 + size_t(HP / 8) * TILE_CH + HP * 4 + 64;
+    const int ctas_per_sm = NC <= 128 ? 4 : 2;
+    const int grid = int(a.NT < int64_t(nsm) * ctas_per_sm ? a.NT : int64_t(nsm) * ctas_per_sm);
+    if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 128>, grid, smem, st, g)); }
+    else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 256>, grid, smem, st, g)); }
+    return rc;
 }
 
-int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG& g, const float* dE, void* ws, cudaStream_t st) {
-    // TODO(tcgen05): BPTT and the front backward still run the fp32 kernels on the shared workspace.
-    return fe_f32_backward(d, x, w, g, dE, ws, st);
+int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG& gr, const float* dE, void* wsp, cudaStream_t st) {
+    TcWs ws = carve_tc(d, wsp);
+    const int NC = nc_of(d.H), HP = hp_of(d.H), NB = nb8_of(d.H);
+    ItemArgs a = make_item_args(d, x, ws);
+    const int nsm = num_sms();
+    int rc;
+    {   // BPTT
+        GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, nullptr, dE, gr.Whh, gr.bhh};
+        const int MB = NC > 128 ? 2 : 1;
+        const size_t smem = size_t(HP / 8) * NC * 16 + size_t(NC / 8) * HP * 16 + size_t(HP / 8) * TILE_CH + size_t(16 * MB) * TILE_CH + HP * 4 + 64;
+        const uint32_t cols = uint32_t(NC + HP + MB * HP);
+        const int ctas_per_sm = cols <= 256 ? 2 : 1;
+        const int grid = int(a.NT < int64_t(nsm) * ctas_per_sm ? a.NT : int64_t(nsm) * ctas_per_sm);
+        if (cols <= 256) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 256>, grid, smem, st, g)); }
+        else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 512>, grid, smem, st, g)); }
+        if (rc != 0) return rc;
+    }
+    cudaError_t ce = cudaMemsetAsync(ws.q, 0, size_t(256) * CP * 4, st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(ws.dwih, 0, size_t(256) * CP * 4, st);
+    if (ce != cudaSuccess) return int(ce);
+    const int64_t nitems = a.NT * d.T;
+    const int grid = int(nitems < nsm ? nitems : nsm);
+    const size_t smem0 = W1_BYTES + size_t(NC / 8) * CP * 16 + A_BYTES + 32 * TILE_CH + CP * 4 + 64;
+    const size_t smem1 = W1_BYTES + 2 * A_BYTES + 32 * TILE_CH + CP * 4 + 64;
+    if (x.dtype == FVAE_BF16) {
+        if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 0>, grid, smem0, st, a)) != 0) return rc;
+        if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 1>, grid, smem1, st, a)) != 0) return rc;
+    } else {
+        if ((rc = launch_smem(tc_front_bwd_kernel<float, 0>, grid, smem0, st, a)) != 0) return rc;
+        if ((rc = launch_smem(tc_front_bwd_kernel<float, 1>, grid, smem1, st, a)) != 0) return rc;
+    }
+    PostArgs p{d.C, d.H, NC, w.ln_w, w.ln_b, w.W1, ws.q, ws.dwih, gr};
+    tc_post_kernel<<<64, 256, 0, st>>>(p); count_launch();
+    return int(cudaGetLastError());
 }
 
 }  // namespace fvae
