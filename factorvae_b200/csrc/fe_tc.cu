@@ -138,185 +138,7 @@ __global__ void tc_prep_kernel(PrepArgs a) {
     for (int j = tid; j < HP; j += nth) a.ws.bhn[j] = j < H ? a.bhh[2 * H + j] : 0.f;
 }
 
-// ---- shared pieces of the item kernels -------------------------------------------------------------------
-struct ItemArgs {
-    const void* x; int64_t seq_pitch, row_pitch;
-    int S, T, C, H, NC, HP; int64_t NT;
-    TcWs ws;
-};
-
-// raw rows [r0, r0+nr) of item (st, t) -> stage[r - r0][C] (zero rows beyond S); one warp per row
-template <typename XT>
-__device__ __forceinline__ void load_rows(const ItemArgs& a, int64_t st, int t, unsigned char* stage, int r0, int nr) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, C = a.C;
-    const int row_bytes = C * int(sizeof(XT));
-    for (int rr = warp; rr < nr; rr += TM / 32) {
-        unsigned char* dst = stage + size_t(rr) * row_bytes;
-        const int64_t s = st * TM + r0 + rr;
-        if (s < a.S) {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + s * a.seq_pitch + int64_t(t) * a.row_pitch);
-            if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0 && (row_bytes & 3) == 0) {
-                for (int w = lane; w < row_bytes / 4; w += 32) reinterpret_cast<uint32_t*>(dst)[w] = reinterpret_cast<const uint32_t*>(src)[w];
-            } else {
-                for (int c = lane; c < C; c += 32) reinterpret_cast<XT*>(dst)[c] = reinterpret_cast<const XT*>(src)[c];
-            }
-        } else {
-            for (int c = lane; c < C; c += 32) reinterpret_cast<XT*>(dst)[c] = XT(0.f);
-        }
-    }
-}
-
-// LayerNorm statistics of one row (fp32, exactly C features) and xhat -> bf16 tile row `trow`; column C := 1
-template <typename XT>
-__device__ __forceinline__ void layernorm_to_tile(const XT* row, int C, unsigned char* tile, int trow) {
-    float sum = 0.f;
-    for (int c = 0; c < C; ++c) sum += float(row[c]);
-    const float mean = sum / float(C);
-    float sq = 0.f;
-    for (int c = 0; c < C; ++c) { const float dlt = float(row[c]) - mean; sq = fmaf(dlt, dlt, sq); }
-    const float rstd = rsqrtf(sq / float(C) + kLnEps);
-#pragma unroll 1
-    for (int ch = 0; ch < KCH; ++ch) {
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = ch * 8 + e;
-            v[e] = (c < C) ? (float(row[c]) - mean) * rstd : (c == C ? 1.f : 0.f);
-        }
-        *reinterpret_cast<uint4*>(tile + tile_off(TM, trow, ch)) =
-            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    }
-}
-
-// stage + normalise the 128 rows of an item.  bf16 panels: one pass of 128 rows; fp32 panels: two passes of
-// 64 rows, so the stage never exceeds one [128 x 160] bf16 tile (40,448 <= 40,960 bytes).
-template <typename XT>
-__device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t st, int t, unsigned char* stage, unsigned char* tile) {
-    constexpr int RPP = sizeof(XT) == 2 ? TM : TM / 2;
-    const int tid = threadIdx.x;
-    for (int r0 = 0; r0 < TM; r0 += RPP) {
-        if (r0 > 0) __syncthreads();
-        load_rows<XT>(a, st, t, stage, r0, RPP);
-        __syncthreads();
-        if (tid >= r0 && tid < r0 + RPP)
-            layernorm_to_tile<XT>(reinterpret_cast<const XT*>(stage) + size_t(tid - r0) * a.C, a.C, tile, tid);
-    }
-}
-
-__device__ __forceinline__ void copy_image(unsigned char* dst, const void* src, uint32_t bytes) {
-    for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
-}
-
-// row GEMM: D[128 x N] (tmem column dcol) = A(K-major tile, 128 rows) . B(K-major image, brows rows)^T over k16 steps
-__device__ __forceinline__ void issue_row_gemm(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t b_addr, uint32_t brows,
-                                               uint32_t N, int k16) {
-    const uint32_t idesc = make_idesc_bf16(TM, N, false, false);
-    for (int ks = 0; ks < k16; ++ks) {
-        const uint64_t ad = make_smem_desc(a_addr + ks * 2 * TILE_CH, TILE_CH, 128);
-        const uint64_t bd = make_smem_desc(b_addr + ks * 2 * (brows * 16), brows * 16, 128);
-        mma_bf16_ss(tmem + dcol, ad, bd, idesc, ks > 0);
-    }
-}
-// weight-gradient GEMM: D[128 x N] (+)= A^T . B with A, B 128-row tiles read MN-major; A's M block starts at chunk a_chunk0
-__device__ __forceinline__ void issue_wgrad(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t a_chunk0, uint32_t b_addr,
-                                            uint32_t N, bool accumulate) {
-    const uint32_t idesc = make_idesc_bf16(TM, N, true, true);
-    for (int ks = 0; ks < TM / 16; ++ks) {
-        const uint64_t ad = make_smem_desc(a_addr + a_chunk0 * TILE_CH + ks * 256, 128, TILE_CH);
-        const uint64_t bd = make_smem_desc(b_addr + ks * 256, 128, TILE_CH);
-        mma_bf16_ss(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
-    }
-}
-
-// ---- K1: front forward ---------------------------------------------------------------------------------------
-template <typename XT>
-__global__ void __launch_bounds__(TM, 1) tc_front_fwd_kernel(ItemArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int C = a.C, NC = a.NC, NCH = NC / 8;
-    unsigned char* sW1 = smem;
-    unsigned char* sWih = sW1 + W1_BYTES;
-    unsigned char* sA1 = sWih + uint32_t(KCH) * NC * 16;
-    unsigned char* sA2 = sA1 + A_BYTES;          // raw-row stage first, then the u tile
-    unsigned char* sTail = sA2 + A_BYTES;
-    float* sB1 = reinterpret_cast<float*>(sTail);
-    float* sBgi = sB1 + CP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBgi + NC);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-
-    copy_image(sW1, a.ws.w1g, W1_BYTES);
-    copy_image(sWih, a.ws.wih, uint32_t(KCH) * NC * 16);
-    for (int i = tid; i < CP; i += TM) sB1[i] = a.ws.b1f[i];
-    for (int i = tid; i < NC; i += TM) sBgi[i] = a.ws.bgi[i];
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    fence_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = uint32_t(warp) * 32u;
-    const int64_t nitems = a.NT * a.T;
-    uint32_t phase = 0;
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, phase ^= 1) {
-        const int64_t st = item / a.T;
-        const int t = int(item % a.T);
-        stage_and_normalize<XT>(a, st, t, sA2, sA1);
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);
-            mma_commit(&bars[0]);
-        }
-        mbar_wait(&bars[0], phase);
-        tc_fence_after_sync();
-        // u = LeakyReLU(pre + b1f) -> bf16 tile (stage is dead: every thread finished its LayerNorm before the sync)
-#pragma unroll 1
-        for (int j = 0; j < CP / 16; ++j) {
-            float v[16];
-            tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int n = j * 16 + e;
-                v[e] = (n == C) ? 1.f : lrelu(v[e] + sB1[n]);
-            }
-            *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j)) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j + 1)) =
-                make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-        }
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            issue_row_gemm(tmem, 256, smem_u32(sA2), smem_u32(sWih), NC, NC, KCH / 2);
-            mma_commit(&bars[1]);
-        }
-        mbar_wait(&bars[1], phase);
-        tc_fence_after_sync();
-        // gi = acc + (b_ih [+ b_hr, b_hz]) -> bf16 GI tile (coalesced 16-byte chunks)
-        {
-            unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-#pragma unroll 1
-            for (int ch = 0; ch < NCH; ++ch) {
-                float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, 256 + ch * 8), v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += sBgi[ch * 8 + e];
-                *reinterpret_cast<uint4*>(gout + tile_off(TM, tid, ch)) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
-        }
-        tc_fence_before_sync();
-        __syncthreads();
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem);
-}
+#include "fe_tc_front.cuh"   // ItemArgs, staging + LayerNorm, K1 front forward, K4 front backward
 
 // ---- K2: GRU forward -------------------------------------------------------------------------------------------
 struct GruArgs {
@@ -583,167 +405,6 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
     if (warp == 0) tmem_dealloc<TCOLS>(tmem);
 }
 
-// ---- K4: front backward (weight gradients) ----------------------------------------------------------------------------
-// MODE 0: Q    += dpre^T [xhat | 1]   (dpre = (dGI . W_ih) * LeakyReLU'(pre))
-// MODE 1: dWih += dGI^T  [u | 1]
-template <typename XT, int MODE>
-__global__ void __launch_bounds__(TM, 1) tc_front_bwd_kernel(ItemArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int C = a.C, NC = a.NC, NCH = NC / 8;
-    const int MBW = NC > 128 ? 2 : 1;
-    unsigned char* sW1 = smem;
-    unsigned char* sNext = sW1 + W1_BYTES;
-    unsigned char* sWihT = sNext;                                  // MODE 0 only: [NCH][CP][16]
-    if (MODE == 0) sNext += uint32_t(NCH) * CP * 16;
-    unsigned char* sA1 = sNext;  sNext += A_BYTES;                 // xhat tile
-    unsigned char* sA2 = sNext;                                    // MODE 1 only: u tile
-    if (MODE == 1) sNext += A_BYTES;
-    unsigned char* sScr = sNext;                                   // raw rows -> dGI tile -> dpre tile (32 chunks)
-    sNext += 32 * TILE_CH;
-    float* sB1 = reinterpret_cast<float*>(sNext);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + CP);        // 0: pre, 1: du, 2: wgrad
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-
-    copy_image(sW1, a.ws.w1g, W1_BYTES);
-    if (MODE == 0) copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
-    for (int i = tid; i < CP; i += TM) sB1[i] = a.ws.b1f[i];
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    fence_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = uint32_t(warp) * 32u;
-    const uint32_t COL_ACC = 160;          // wgrad accumulators: [160, 480)
-    const int64_t nitems = a.NT * a.T;
-    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
-    bool pending = false, started = false;
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int64_t st = item / a.T;
-        const int t = int(item % a.T);
-        if (pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }       // tiles are free again
-        stage_and_normalize<XT>(a, st, t, sScr, sA1);
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);   // pre
-            mma_commit(&bars[0]);
-        }
-        // dGI tile of this item -> scratch (the raw rows are dead), overlapping the MMA
-        {
-            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-            for (int ch = 0; ch < NCH; ++ch)
-                *reinterpret_cast<uint4*>(sScr + tile_off(TM, tid, ch)) = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, ch));
-        }
-        mbar_wait(&bars[0], ph0);
-        ph0 ^= 1;
-        tc_fence_after_sync();
-        if (MODE == 1) {
-            // u = LeakyReLU(pre + b1f) -> bf16 tile, column C := 1
-#pragma unroll 1
-            for (int j = 0; j < CP / 16; ++j) {
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int n = j * 16 + e;
-                    v[e] = (n == C) ? 1.f : lrelu(v[e] + sB1[n]);
-                }
-                *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j)) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                *reinterpret_cast<uint4*>(sA2 + tile_off(TM, tid, 2 * j + 1)) =
-                    make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-            }
-            fence_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                for (int mb = 0; mb < MBW; ++mb)
-                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA2), CP, started);
-                mma_commit(&bars[2]);
-            }
-        } else {
-            // LeakyReLU' mask of my row: 160 bits
-            uint32_t mask[CP / 32];
-#pragma unroll
-            for (int w = 0; w < CP / 32; ++w) mask[w] = 0u;
-#pragma unroll
-            for (int j = 0; j < CP / 16; ++j) {
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int n = j * 16 + e;
-                    if (v[e] + sB1[n] > 0.f) mask[n >> 5] |= 1u << (n & 31);
-                }
-            }
-            fence_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                issue_row_gemm(tmem, 0, smem_u32(sScr), smem_u32(sWihT), CP, CP, NC / 16);     // du = dGI . W_ih
-                mma_commit(&bars[1]);
-            }
-            mbar_wait(&bars[1], ph1);
-            ph1 ^= 1;
-            tc_fence_after_sync();
-            // dpre = du * LeakyReLU'(pre) -> bf16 tile over the (dead) dGI tile
-#pragma unroll
-            for (int j = 0; j < CP / 16; ++j) {
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int n = j * 16 + e;
-                    v[e] *= ((mask[n >> 5] >> (n & 31)) & 1u) ? 1.f : kLeakySlope;
-                }
-                *reinterpret_cast<uint4*>(sScr + tile_off(TM, tid, 2 * j)) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                *reinterpret_cast<uint4*>(sScr + tile_off(TM, tid, 2 * j + 1)) =
-                    make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-            }
-            fence_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                for (int mb = 0; mb < 2; ++mb)
-                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA1), CP, started);
-                mma_commit(&bars[2]);
-            }
-        }
-        started = true;
-        pending = true;
-    }
-    if (pending) mbar_wait(&bars[2], ph2);
-    tc_fence_after_sync();
-    if (started) {
-        float* outbuf = MODE == 0 ? a.ws.q : a.ws.dwih;
-        const int nblk = MODE == 0 ? 2 : MBW;
-        for (int mb = 0; mb < nblk; ++mb) {
-            const int row = mb * 128 + tid;
-            const bool ok = MODE == 0 ? row < C : row < NC;
-            for (int j = 0; j < CP / 16; ++j) {
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + j * 16), v);
-                if (ok) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) atomicAdd(outbuf + size_t(row) * CP + j * 16 + e, v[e]);
-                }
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
 // ---- K5: assemble the parameter gradients from Q / dWih ---------------------------------------------------------------------
 struct PostArgs {
     int C, H, NC;
@@ -782,6 +443,8 @@ __global__ void tc_post_kernel(PostArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
+constexpr size_t kMaxSmem = 227 * 1024;
+
 int num_sms() {
     int dev = 0, n = 148;
     cudaGetDevice(&dev);
@@ -794,7 +457,7 @@ int launch_smem(KernelT k, int grid, size_t smem, cudaStream_t st, const ItemArg
     if (smem > 227 * 1024) return FVAE_ERR_LIMIT;
     cudaError_t ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (ce != cudaSuccess) return int(ce);
-    k<<<grid, TM, smem, st>>>(a); count_launch();
+    k<<<grid, NTH, smem, st>>>(a); count_launch();
     return int(cudaGetLastError());
 }
 template <typename KernelT>
@@ -811,6 +474,7 @@ ItemArgs make_item_args(const FeDims& d, const fvae_panel& x, const TcWs& ws) {
     a.x = x.data; a.seq_pitch = x.seq_pitch; a.row_pitch = x.row_pitch;
     a.S = d.S; a.T = d.T; a.C = d.C; a.H = d.H; a.NC = nc_of(d.H); a.HP = hp_of(d.H);
     a.NT = (int64_t(d.S) + TM - 1) / TM;
+    a.prefetch = 0;
     a.ws = ws;
     return a;
 }
@@ -847,7 +511,10 @@ int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, 
     int rc;
     {
         const int grid = int(nitems < nsm ? nitems : nsm);
-        const size_t smem = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + (CP + NC) * 4 + 64;
+        const size_t tail = (CP + NC + 4 * TM) * 4 + 64;
+        const size_t with_stage = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + STAGE_BYTES + tail;
+        a.prefetch = (x.dtype == FVAE_BF16 && with_stage <= kMaxSmem) ? 1 : 0;
+        const size_t smem = a.prefetch ? with_stage : W1_BYTES + size_t(KCH) * NC * 16 + A_BYTES + STAGE_BYTES + tail;
         if (x.dtype == FVAE_BF16) rc = launch_smem(tc_front_fwd_kernel<__nv_bfloat16>, grid, smem, st, a);
         else rc = launch_smem(tc_front_fwd_kernel<float>, grid, smem, st, a);
         if (rc != 0) return rc;
@@ -883,12 +550,19 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     if (ce != cudaSuccess) return int(ce);
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
-    const size_t smem0 = W1_BYTES + size_t(NC / 8) * CP * 16 + A_BYTES + 32 * TILE_CH + CP * 4 + 64;
-    const size_t smem1 = W1_BYTES + 2 * A_BYTES + 32 * TILE_CH + CP * 4 + 64;
-    if (x.dtype == FVAE_BF16) {
+    const size_t tail = (CP + 4 * TM) * 4 + 64;
+    const size_t base0 = W1_BYTES + size_t(NC / 8) * CP * 16 + A_BYTES + 32 * TILE_CH + tail;
+    const size_t base1 = W1_BYTES + 2 * A_BYTES + size_t(NC > 128 ? 32 : 21) * TILE_CH + tail;
+    const bool bf = x.dtype == FVAE_BF16;
+    const bool pf0 = bf && base0 + STAGE_BYTES <= kMaxSmem, pf1 = bf && base1 + STAGE_BYTES <= kMaxSmem;
+    const size_t smem0 = base0 + (pf0 ? STAGE_BYTES : 0), smem1 = base1 + (pf1 ? STAGE_BYTES : 0);
+    if (bf) {
+        a.prefetch = pf0;
         if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 0>, grid, smem0, st, a)) != 0) return rc;
+        a.prefetch = pf1;
         if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 1>, grid, smem1, st, a)) != 0) return rc;
     } else {
+        a.prefetch = 0;
         if ((rc = launch_smem(tc_front_bwd_kernel<float, 0>, grid, smem0, st, a)) != 0) return rc;
         if ((rc = launch_smem(tc_front_bwd_kernel<float, 1>, grid, smem1, st, a)) != 0) return rc;
     }

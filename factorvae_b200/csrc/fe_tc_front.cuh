@@ -1,0 +1,483 @@
+// Item kernels of the tensor-core FeatureExtractor (included by fe_tc.cu inside namespace fvae::<anon>):
+//   K1 tc_front_fwd_kernel : LayerNorm -> GEMM1 -> LeakyReLU -> GEMM2 -> GI tile        (reference module.py:26-30)
+//   K4 tc_front_bwd_kernel : recompute, du = dGI . W_ih, dpre, weight-gradient GEMMs    (autograd of the same)
+// An item is (sequence tile of 128 stocks, time step): 128 panel rows = one UMMA M = the 128 TMEM lanes.
+// 256 threads per CTA: thread (row = tid & 127, half = tid >> 7) owns 80 of the 160 columns of its row in
+// LayerNorm and in every epilogue (warps w and w+4 read the same 32 TMEM lanes, different columns).
+#pragma once
+
+struct ItemArgs {
+    const void* x; int64_t seq_pitch, row_pitch;
+    int S, T, C, H, NC, HP; int64_t NT;
+    int prefetch;            // 1: dedicated raw-row stage, next item's rows are fetched during this item's MMAs
+    TcWs ws;
+};
+
+constexpr int NTH = 256;
+constexpr int HALF_COLS = CP / 2;            // 80 columns per thread
+constexpr int HALF_CH = KCH / 2;             // 10 chunks per thread
+
+__device__ __forceinline__ void copy_image(unsigned char* dst, const void* src, uint32_t bytes) {
+    for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
+// row GEMM: D[128 x N] (tmem column dcol) = A(K-major tile, 128 rows) . B(K-major image, brows rows)^T over k16 steps
+__device__ __forceinline__ void issue_row_gemm(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t b_addr, uint32_t brows,
+                                               uint32_t N, int k16) {
+    const uint32_t idesc = make_idesc_bf16(TM, N, false, false);
+    for (int ks = 0; ks < k16; ++ks) {
+        const uint64_t ad = make_smem_desc(a_addr + ks * 2 * TILE_CH, TILE_CH, 128);
+        const uint64_t bd = make_smem_desc(b_addr + ks * 2 * (brows * 16), brows * 16, 128);
+        mma_bf16_ss(tmem + dcol, ad, bd, idesc, ks > 0);
+    }
+}
+// weight-gradient GEMM: D[128 x N] (+)= A^T . B with A, B 128-row tiles read MN-major; A's M block starts at chunk a_chunk0
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t a_chunk0, uint32_t b_addr,
+                                            uint32_t N, bool accumulate) {
+    const uint32_t idesc = make_idesc_bf16(TM, N, true, true);
+    for (int ks = 0; ks < TM / 16; ++ks) {
+        const uint64_t ad = make_smem_desc(a_addr + a_chunk0 * TILE_CH + ks * 256, 128, TILE_CH);
+        const uint64_t bd = make_smem_desc(b_addr + ks * 256, 128, TILE_CH);
+        mma_bf16_ss(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+    }
+}
+
+// ---- staging of raw panel rows ------------------------------------------------------------------------------
+// A row of the panel (C*2 = 316 B in bf16) starts at a 2- or 4-byte aligned address, so it is copied as the
+// 16-byte aligned window that covers it: slot = round16(row bytes) + 16 bytes, fetched with cp.async.cg 16 B
+// (LDGSTS.128: no register staging, every row of the item in flight at once).  The consumer adds
+// (row address & 15) to find its first element.  A window that would run past the end of the panel
+// (last rows only) falls back to element copies.  The slot pitch (336 / 656 B) is an odd multiple of 16, so
+// thread-per-row LDS.128 reads are bank-conflict free.
+constexpr uint32_t STAGE_BYTES = 43008;      // 128 slots x 336 B (bf16 rows) >= 64 slots x 656 B (fp32 rows)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+template <typename XT>
+__device__ __forceinline__ uint32_t slot_bytes(int C) {
+    uint32_t s = ((uint32_t(C) * sizeof(XT) + 15u) & ~15u) + 16u;
+    if (((s >> 4) & 1u) == 0u) s += 16u;       // odd number of 16-byte pieces
+    return s;
+}
+template <typename XT>
+__device__ __forceinline__ const unsigned char* row_ptr(const ItemArgs& a, int64_t s, int t) {
+    return reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + s * a.seq_pitch + int64_t(t) * a.row_pitch);
+}
+template <typename XT>
+struct Rows { static constexpr int PER_PASS = sizeof(XT) == 2 ? TM : TM / 2; };
+
+// rows [r0, r0 + PER_PASS) of item (st, t) -> slots (zero rows beyond S); one warp per row, asynchronous
+template <typename XT>
+__device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, int t, unsigned char* stage, int r0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, C = a.C;
+    const uint32_t slot = slot_bytes<XT>(C);
+    const int npieces = int(slot / 16);
+    const unsigned char* x_end = row_ptr<XT>(a, a.S - 1, a.T - 1) + size_t(C) * sizeof(XT);
+    for (int rr = warp; rr < Rows<XT>::PER_PASS; rr += NTH / 32) {
+        unsigned char* dst = stage + size_t(rr) * slot;
+        const int64_t s = st * TM + r0 + rr;
+        if (s < a.S) {
+            const unsigned char* src = row_ptr<XT>(a, s, t);
+            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
+            if (a0 + slot <= x_end) {
+                for (int pc = lane; pc < npieces; pc += 32) cp_async16(smem_u32(dst + pc * 16), a0 + pc * 16);
+            } else {
+                XT* d2 = reinterpret_cast<XT*>(dst + (src - a0));
+                for (int c = lane; c < C; c += 32) d2[c] = reinterpret_cast<const XT*>(src)[c];
+            }
+        } else {
+            for (int pc = lane; pc < npieces; pc += 32) *reinterpret_cast<uint4*>(dst + pc * 16) = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+// ---- my 80 features of my row, realigned from the slot into registers -------------------------------------------
+template <int W>
+__device__ __forceinline__ void realign_words(const uint4* pieces, uint32_t (&w)[HALF_COLS / 2]) {
+    uint32_t q[44];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+        if (i < 10 || W > 0) {
+            const uint4 v = pieces[i];
+            q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+        } else {
+            q[4 * i] = q[4 * i + 1] = q[4 * i + 2] = q[4 * i + 3] = 0u;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < HALF_COLS / 2; ++j) w[j] = q[j + W];
+}
+template <int W>
+__device__ __forceinline__ void realign_floats(const uint4* pieces, float (&v)[HALF_COLS]) {
+    uint32_t q[84];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) {
+        if (i < 20 || W > 0) {
+            const uint4 u = pieces[i];
+            q[4 * i] = u.x; q[4 * i + 1] = u.y; q[4 * i + 2] = u.z; q[4 * i + 3] = u.w;
+        } else {
+            q[4 * i] = q[4 * i + 1] = q[4 * i + 2] = q[4 * i + 3] = 0u;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < HALF_COLS; ++j) v[j] = __uint_as_float(q[j + W]);
+}
+
+// features [80*half, 80*half + 80) of the row stored in `slot` (first element at byte `off`) -> fp32 registers
+__device__ __forceinline__ void fetch_half(const __nv_bfloat16*, const unsigned char* slot, uint32_t off, int half, float (&v)[HALF_COLS]) {
+    uint32_t w[HALF_COLS / 2];
+    if ((off & 3u) == 0u) {
+        const uint4* pieces = reinterpret_cast<const uint4*>(slot) + 10 * half;
+        switch (off >> 2) {
+            case 0: realign_words<0>(pieces, w); break;
+            case 1: realign_words<1>(pieces, w); break;
+            case 2: realign_words<2>(pieces, w); break;
+            default: realign_words<3>(pieces, w); break;
+        }
+    } else {       // 2-byte aligned rows (odd pitch): element loads
+        const unsigned short* e = reinterpret_cast<const unsigned short*>(slot + off) + HALF_COLS * half;
+#pragma unroll
+        for (int j = 0; j < HALF_COLS / 2; ++j) w[j] = uint32_t(e[2 * j]) | (uint32_t(e[2 * j + 1]) << 16);
+    }
+#pragma unroll
+    for (int j = 0; j < HALF_COLS / 2; ++j) {
+        v[2 * j] = __uint_as_float(w[j] << 16);
+        v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ void fetch_half(const float*, const unsigned char* slot, uint32_t off, int half, float (&v)[HALF_COLS]) {
+    const uint4* pieces = reinterpret_cast<const uint4*>(slot) + 20 * half;
+    switch ((off >> 2) & 3u) {
+        case 0: realign_floats<0>(pieces, v); break;
+        case 1: realign_floats<1>(pieces, v); break;
+        case 2: realign_floats<2>(pieces, v); break;
+        default: realign_floats<3>(pieces, v); break;
+    }
+}
+
+// LayerNorm of the rows staged for pass `r0` (statistics in fp32 over exactly C features) -> xhat bf16 tile,
+// column C := 1.  Called by all 256 threads (two block barriers inside).
+template <typename XT>
+__device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, int t, const unsigned char* stage, int r0,
+                                               unsigned char* tile, float* sStat) {
+    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7, C = a.C;
+    const bool active = row >= r0 && row < r0 + Rows<XT>::PER_PASS;
+    float v[HALF_COLS];
+    float part = 0.f;
+    if (active) {
+        const int64_t s = st * TM + row;
+        const uint32_t off = s < a.S ? uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u) : 0u;
+        fetch_half(static_cast<const XT*>(nullptr), stage + size_t(row - r0) * slot_bytes<XT>(C), off, half, v);
+#pragma unroll
+        for (int j = 0; j < HALF_COLS; ++j) {
+            if (HALF_COLS * half + j >= C) v[j] = 0.f;
+            part += v[j];
+        }
+        sStat[half * TM + row] = part;
+    }
+    __syncthreads();
+    float mean = 0.f;
+    if (active) {
+        mean = (sStat[row] + sStat[TM + row]) / float(C);
+        part = 0.f;
+#pragma unroll
+        for (int j = 0; j < HALF_COLS; ++j) {
+            const float dlt = (HALF_COLS * half + j < C) ? v[j] - mean : 0.f;
+            part = fmaf(dlt, dlt, part);
+        }
+        sStat[2 * TM + half * TM + row] = part;
+    }
+    __syncthreads();
+    if (active) {
+        const float rstd = rsqrtf((sStat[2 * TM + row] + sStat[3 * TM + row]) / float(C) + kLnEps);
+#pragma unroll
+        for (int ch = 0; ch < HALF_CH; ++ch) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int j = ch * 8 + e, c = HALF_COLS * half + j;
+                o[e] = (c < C) ? (v[j] - mean) * rstd : (c == C ? 1.f : 0.f);
+            }
+            *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
+                make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+    }
+}
+
+// all loads of one item (bf16: one pass; fp32: the given pass)
+template <typename XT>
+__device__ __forceinline__ void issue_item_loads(const ItemArgs& a, int64_t item, unsigned char* stage, int r0) {
+    load_rows_async<XT>(a, item / a.T, int(item % a.T), stage, r0);
+}
+
+// stage (unless already prefetched) + LayerNorm of one item -> xhat tile
+template <typename XT>
+__device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t item, unsigned char* stage, unsigned char* tile,
+                                                    float* sStat, bool already_issued) {
+    const int64_t st = item / a.T;
+    const int t = int(item % a.T);
+    for (int r0 = 0; r0 < TM; r0 += Rows<XT>::PER_PASS) {
+        if (r0 > 0) __syncthreads();
+        if (!(already_issued && r0 == 0)) load_rows_async<XT>(a, st, t, stage, r0);
+        cp_async_wait_all();
+        __syncthreads();
+        layernorm_pass<XT>(a, st, t, stage, r0, tile, sStat);
+    }
+}
+
+// u = LeakyReLU(acc + b1f) for my 80 columns -> bf16 tile, column C := 1
+__device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, int half, int row, int C, const float* sB1, unsigned char* tile) {
+#pragma unroll 1
+    for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
+        const int j = half * (HALF_COLS / 16) + jj;
+        float v[16];
+        tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int n = j * 16 + e;
+            v[e] = (n == C) ? 1.f : lrelu(v[e] + sB1[n]);
+        }
+        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, 2 * j)) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, 2 * j + 1)) =
+            make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+    }
+}
+
+// ---- K1: front forward ---------------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
+    const int C = a.C, NC = a.NC, NCH = NC / 8;
+    unsigned char* sW1 = smem;
+    unsigned char* sWih = sW1 + W1_BYTES;
+    unsigned char* sA1 = sWih + uint32_t(KCH) * NC * 16;
+    unsigned char* sA2 = sA1 + A_BYTES;          // u tile; doubles as the raw-row stage when there is no dedicated one
+    unsigned char* sStage = a.prefetch ? sA2 + A_BYTES : sA2;
+    unsigned char* sTail = a.prefetch ? sStage + STAGE_BYTES : sA2 + STAGE_BYTES;
+    float* sB1 = reinterpret_cast<float*>(sTail);
+    float* sBgi = sB1 + CP;
+    float* sStat = sBgi + NC;                    // [4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 4 * TM);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+    copy_image(sW1, a.ws.w1g, W1_BYTES);
+    copy_image(sWih, a.ws.wih, uint32_t(KCH) * NC * 16);
+    for (int i = tid; i < CP; i += NTH) sB1[i] = a.ws.b1f[i];
+    for (int i = tid; i < NC; i += NTH) sBgi[i] = a.ws.bgi[i];
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+    const int64_t nitems = a.NT * a.T;
+    const bool prefetch = a.prefetch != 0 && sizeof(XT) == 2;
+    uint32_t phase = 0;
+    if (prefetch && int64_t(blockIdx.x) < nitems) issue_item_loads<XT>(a, blockIdx.x, sStage, 0);
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, phase ^= 1) {
+        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, prefetch);
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);
+            mma_commit(&bars[0]);
+        }
+        if (prefetch && item + gridDim.x < nitems) issue_item_loads<XT>(a, item + gridDim.x, sStage, 0);   // stage is free
+        mbar_wait(&bars[0], phase);
+        tc_fence_after_sync();
+        epilogue_u(tmem, lane_base, half, row, C, sB1, sA2);
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            issue_row_gemm(tmem, 256, smem_u32(sA2), smem_u32(sWih), NC, NC, KCH / 2);
+            mma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], phase);
+        tc_fence_after_sync();
+        // gi = acc + (b_ih [+ b_hr, b_hz]) -> bf16 GI tile (coalesced 16-byte chunks); halves split the chunks
+        {
+            unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
+            const int ch0 = half == 0 ? 0 : (NCH + 1) / 2, ch1 = half == 0 ? (NCH + 1) / 2 : NCH;
+#pragma unroll 1
+            for (int ch = ch0; ch < ch1; ++ch) {
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, 256 + ch * 8), v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += sBgi[ch * 8 + e];
+                *reinterpret_cast<uint4*>(gout + tile_off(TM, row, ch)) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---- K4: front backward (weight gradients) ----------------------------------------------------------------------------
+// MODE 0: Q    += dpre^T [xhat | 1]   (dpre = (dGI . W_ih) * LeakyReLU'(pre))
+// MODE 1: dWih += dGI^T  [u | 1]
+template <typename XT, int MODE>
+__global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
+    const int C = a.C, NC = a.NC, NCH = NC / 8;
+    const int MBW = NC > 128 ? 2 : 1;
+    const uint32_t scr_chunks = (MODE == 0 || MBW == 2) ? 32u : 21u;     // MODE 1, one M block: dGI tile + over-read <= 16 chunks, stage 21
+    unsigned char* sW1 = smem;
+    unsigned char* sNext = sW1 + W1_BYTES;
+    unsigned char* sWihT = sNext;                                  // MODE 0 only: [NCH][CP][16]
+    if (MODE == 0) sNext += uint32_t(NCH) * CP * 16;
+    unsigned char* sA1 = sNext;  sNext += A_BYTES;                 // xhat tile
+    unsigned char* sA2 = sNext;                                    // MODE 1 only: u tile
+    if (MODE == 1) sNext += A_BYTES;
+    unsigned char* sScr = sNext;                                   // [raw rows ->] dGI tile -> dpre tile
+    sNext += scr_chunks * TILE_CH;
+    unsigned char* sStage = a.prefetch ? sNext : sScr;
+    if (a.prefetch) sNext += STAGE_BYTES;
+    float* sB1 = reinterpret_cast<float*>(sNext);
+    float* sStat = sB1 + CP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 4 * TM);  // 0: pre, 1: du, 2: wgrad
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    copy_image(sW1, a.ws.w1g, W1_BYTES);
+    if (MODE == 0) copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
+    for (int i = tid; i < CP; i += NTH) sB1[i] = a.ws.b1f[i];
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+    const uint32_t COL_ACC = 160;          // wgrad accumulators: [160, 480)
+    const int64_t nitems = a.NT * a.T;
+    const bool prefetch = a.prefetch != 0 && sizeof(XT) == 2;
+    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
+    bool pending = false, started = false;
+    if (prefetch && int64_t(blockIdx.x) < nitems) issue_item_loads<XT>(a, blockIdx.x, sStage, 0);
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        if (pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }       // xhat / u / scratch tiles are free again
+        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, prefetch);
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);   // pre
+            mma_commit(&bars[0]);
+        }
+        if (prefetch && item + gridDim.x < nitems) issue_item_loads<XT>(a, item + gridDim.x, sStage, 0);
+        // dGI tile of this item -> scratch (any raw rows there are dead), overlapping the MMA
+        {
+            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
+            for (int ch = half; ch < NCH; ch += 2)
+                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, ch)) = *reinterpret_cast<const uint4*>(gin + tile_off(TM, row, ch));
+        }
+        mbar_wait(&bars[0], ph0);
+        ph0 ^= 1;
+        tc_fence_after_sync();
+        if (MODE == 1) {
+            epilogue_u(tmem, lane_base, half, row, C, sB1, sA2);
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                for (int mb = 0; mb < MBW; ++mb)
+                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA2), CP, started);
+                mma_commit(&bars[2]);
+            }
+        } else {
+            // LeakyReLU' mask of my 80 columns
+            uint32_t mask[3] = {0u, 0u, 0u};
+#pragma unroll
+            for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
+                const int j = half * (HALF_COLS / 16) + jj;
+                float v[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int b = jj * 16 + e;
+                    if (v[e] + sB1[j * 16 + e] > 0.f) mask[b >> 5] |= 1u << (b & 31);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                issue_row_gemm(tmem, 0, smem_u32(sScr), smem_u32(sWihT), CP, CP, NC / 16);     // du = dGI . W_ih
+                mma_commit(&bars[1]);
+            }
+            mbar_wait(&bars[1], ph1);
+            ph1 ^= 1;
+            tc_fence_after_sync();
+            // dpre = du * LeakyReLU'(pre) -> bf16 tile over the (dead) dGI tile
+#pragma unroll
+            for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
+                const int j = half * (HALF_COLS / 16) + jj;
+                float v[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int b = jj * 16 + e;
+                    v[e] *= ((mask[b >> 5] >> (b & 31)) & 1u) ? 1.f : kLeakySlope;
+                }
+                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, 2 * j)) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, 2 * j + 1)) =
+                    make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                for (int mb = 0; mb < 2; ++mb)
+                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA1), CP, started);
+                mma_commit(&bars[2]);
+            }
+        }
+        started = true;
+        pending = true;
+    }
+    if (pending) mbar_wait(&bars[2], ph2);
+    tc_fence_after_sync();
+    if (started) {
+        float* outbuf = MODE == 0 ? a.ws.q : a.ws.dwih;
+        const int nblk = MODE == 0 ? 2 : MBW;
+        for (int mb = 0; mb < nblk; ++mb) {
+            const int orow = mb * 128 + row;
+            const bool ok = MODE == 0 ? orow < C : orow < NC;
+            for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
+                const int j = half * (HALF_COLS / 16) + jj;
+                float v[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + j * 16), v);
+                if (ok) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(outbuf + size_t(orow) * CP + j * 16 + e, v[e]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
