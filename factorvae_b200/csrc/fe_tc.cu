@@ -511,7 +511,7 @@ int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, 
     int rc;
     {
         const int grid = int(nitems < nsm ? nitems : nsm);
-        const size_t tail = (CP + NC + 4 * TM) * 4 + 64;
+        const size_t tail = (CP + NC + 2 * NSPLIT * TM) * 4 + 64;
         const size_t with_stage = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + STAGE_BYTES + tail;
         a.prefetch = (x.dtype == FVAE_BF16 && with_stage <= kMaxSmem) ? 1 : 0;
         const size_t smem = a.prefetch ? with_stage : W1_BYTES + size_t(KCH) * NC * 16 + A_BYTES + STAGE_BYTES + tail;
@@ -550,7 +550,7 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     if (ce != cudaSuccess) return int(ce);
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
-    const size_t tail = (CP + 4 * TM) * 4 + 64;
+    const size_t tail = (CP + 2 * NSPLIT * TM) * 4 + 64;
     const size_t base0 = W1_BYTES + size_t(NC / 8) * CP * 16 + A_BYTES + 32 * TILE_CH + tail;
     const size_t base1 = W1_BYTES + 2 * A_BYTES + size_t(NC > 128 ? 32 : 21) * TILE_CH + tail;
     const bool bf = x.dtype == FVAE_BF16;

@@ -2,8 +2,9 @@
 //   K1 tc_front_fwd_kernel : LayerNorm -> GEMM1 -> LeakyReLU -> GEMM2 -> GI tile        (reference module.py:26-30)
 //   K4 tc_front_bwd_kernel : recompute, du = dGI . W_ih, dpre, weight-gradient GEMMs    (autograd of the same)
 // An item is (sequence tile of 128 stocks, time step): 128 panel rows = one UMMA M = the 128 TMEM lanes.
-// 256 threads per CTA: thread (row = tid & 127, half = tid >> 7) owns 80 of the 160 columns of its row in
-// LayerNorm and in every epilogue (warps w and w+4 read the same 32 TMEM lanes, different columns).
+// 512 threads per CTA: thread (row = tid & 127, part = tid >> 7) owns 40 of the 160 columns of its row in
+// LayerNorm and in every epilogue (warps w, w+4, w+8, w+12 read the same 32 TMEM lanes, different columns);
+// 16 resident warps hide the LDS / TMEM-load / MUFU latencies that 4 warps cannot.
 #pragma once
 
 struct ItemArgs {
@@ -13,9 +14,12 @@ struct ItemArgs {
     TcWs ws;
 };
 
-constexpr int NTH = 256;
-constexpr int HALF_COLS = CP / 2;            // 80 columns per thread
-constexpr int HALF_CH = KCH / 2;             // 10 chunks per thread
+constexpr int NSPLIT = 4;                    // column parts per row
+constexpr int NTH = TM * NSPLIT;             // 512 threads
+constexpr int HALF_COLS = CP / NSPLIT;       // 40 columns per thread
+constexpr int HALF_CH = KCH / NSPLIT;        // 5 chunks per thread
+constexpr int NPW = HALF_COLS / 2 / 4 + 1;   // 16-byte pieces a thread may touch for its bf16 words (6)
+constexpr int NPF = HALF_COLS / 4 + 1;       // ... for its fp32 values (11)
 
 __device__ __forceinline__ void copy_image(unsigned char* dst, const void* src, uint32_t bytes) {
     for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
@@ -71,16 +75,34 @@ __device__ __forceinline__ const unsigned char* row_ptr(const ItemArgs& a, int64
 template <typename XT>
 struct Rows { static constexpr int PER_PASS = sizeof(XT) == 2 ? TM : TM / 2; };
 
-// rows [r0, r0 + PER_PASS) of item (st, t) -> slots (zero rows beyond S); one warp per row, asynchronous
+// rows [r0, r0 + PER_PASS) of item (st, t) -> slots (zero rows beyond S); one warp per row, asynchronous.
+// Fast path (every row of the pass exists and no 16-byte window can cross the end of the panel): lane = piece,
+// pointer increments only.
 template <typename XT>
 __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, int t, unsigned char* stage, int r0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, C = a.C;
     const uint32_t slot = slot_bytes<XT>(C);
     const int npieces = int(slot / 16);
+    constexpr int NW = NTH / 32;
+    const int64_t s0 = st * TM + r0;
+    if (s0 + Rows<XT>::PER_PASS + 1 <= a.S && npieces <= 64) {
+        const unsigned char* src = row_ptr<XT>(a, s0 + warp, t);
+        const int64_t step = a.seq_pitch * int64_t(sizeof(XT)) * NW;
+        uint32_t dst = smem_u32(stage) + uint32_t(warp) * slot + uint32_t(lane) * 16u;
+#pragma unroll 4
+        for (int rr = warp; rr < Rows<XT>::PER_PASS; rr += NW) {
+            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15)) + lane * 16;
+            if (lane < npieces) cp_async16(dst, a0);
+            if (lane + 32 < npieces) cp_async16(dst + 512u, a0 + 512);
+            src += step;
+            dst += NW * slot;
+        }
+        return;
+    }
     const unsigned char* x_end = row_ptr<XT>(a, a.S - 1, a.T - 1) + size_t(C) * sizeof(XT);
-    for (int rr = warp; rr < Rows<XT>::PER_PASS; rr += NTH / 32) {
+    for (int rr = warp; rr < Rows<XT>::PER_PASS; rr += NW) {
         unsigned char* dst = stage + size_t(rr) * slot;
-        const int64_t s = st * TM + r0 + rr;
+        const int64_t s = s0 + rr;
         if (s < a.S) {
             const unsigned char* src = row_ptr<XT>(a, s, t);
             const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
@@ -96,13 +118,13 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
     }
 }
 
-// ---- my 80 features of my row, realigned from the slot into registers -------------------------------------------
+// ---- my 40 features of my row, realigned from the slot into registers -------------------------------------------
 template <int W>
 __device__ __forceinline__ void realign_words(const uint4* pieces, uint32_t (&w)[HALF_COLS / 2]) {
-    uint32_t q[44];
+    uint32_t q[4 * NPW];
 #pragma unroll
-    for (int i = 0; i < 11; ++i) {
-        if (i < 10 || W > 0) {
+    for (int i = 0; i < NPW; ++i) {
+        if (i < NPW - 1 || W > 0) {
             const uint4 v = pieces[i];
             q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
         } else {
@@ -114,10 +136,10 @@ __device__ __forceinline__ void realign_words(const uint4* pieces, uint32_t (&w)
 }
 template <int W>
 __device__ __forceinline__ void realign_floats(const uint4* pieces, float (&v)[HALF_COLS]) {
-    uint32_t q[84];
+    uint32_t q[4 * NPF];
 #pragma unroll
-    for (int i = 0; i < 21; ++i) {
-        if (i < 20 || W > 0) {
+    for (int i = 0; i < NPF; ++i) {
+        if (i < NPF - 1 || W > 0) {
             const uint4 u = pieces[i];
             q[4 * i] = u.x; q[4 * i + 1] = u.y; q[4 * i + 2] = u.z; q[4 * i + 3] = u.w;
         } else {
@@ -128,11 +150,11 @@ __device__ __forceinline__ void realign_floats(const uint4* pieces, float (&v)[H
     for (int j = 0; j < HALF_COLS; ++j) v[j] = __uint_as_float(q[j + W]);
 }
 
-// features [80*half, 80*half + 80) of the row stored in `slot` (first element at byte `off`) -> fp32 registers
+// features [40*part, 40*part + 40) of the row stored in `slot` (first element at byte `off`) -> fp32 registers
 __device__ __forceinline__ void fetch_half(const __nv_bfloat16*, const unsigned char* slot, uint32_t off, int half, float (&v)[HALF_COLS]) {
     uint32_t w[HALF_COLS / 2];
     if ((off & 3u) == 0u) {
-        const uint4* pieces = reinterpret_cast<const uint4*>(slot) + 10 * half;
+        const uint4* pieces = reinterpret_cast<const uint4*>(slot) + (HALF_COLS / 8) * half;
         switch (off >> 2) {
             case 0: realign_words<0>(pieces, w); break;
             case 1: realign_words<1>(pieces, w); break;
@@ -151,7 +173,7 @@ __device__ __forceinline__ void fetch_half(const __nv_bfloat16*, const unsigned 
     }
 }
 __device__ __forceinline__ void fetch_half(const float*, const unsigned char* slot, uint32_t off, int half, float (&v)[HALF_COLS]) {
-    const uint4* pieces = reinterpret_cast<const uint4*>(slot) + 20 * half;
+    const uint4* pieces = reinterpret_cast<const uint4*>(slot) + (HALF_COLS / 4) * half;
     switch ((off >> 2) & 3u) {
         case 0: realign_floats<0>(pieces, v); break;
         case 1: realign_floats<1>(pieces, v); break;
@@ -161,51 +183,56 @@ __device__ __forceinline__ void fetch_half(const float*, const unsigned char* sl
 }
 
 // LayerNorm of the rows staged for pass `r0` (statistics in fp32 over exactly C features) -> xhat bf16 tile,
-// column C := 1.  Called by all 256 threads (two block barriers inside).
+// column C := 1.  Called by all threads (two block barriers inside).  Only the thread whose 40 columns
+// straddle C pays for masking.
 template <typename XT>
 __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, int t, const unsigned char* stage, int r0,
                                                unsigned char* tile, float* sStat) {
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7, C = a.C;
     const bool active = row >= r0 && row < r0 + Rows<XT>::PER_PASS;
+    const int c0 = HALF_COLS * half;
+    const bool partial = c0 + HALF_COLS > C;            // warp-uniform
     float v[HALF_COLS];
     float part = 0.f;
     if (active) {
         const int64_t s = st * TM + row;
         const uint32_t off = s < a.S ? uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u) : 0u;
         fetch_half(static_cast<const XT*>(nullptr), stage + size_t(row - r0) * slot_bytes<XT>(C), off, half, v);
+        if (partial) {
 #pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) {
-            if (HALF_COLS * half + j >= C) v[j] = 0.f;
-            part += v[j];
+            for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = 0.f;
         }
+#pragma unroll
+        for (int j = 0; j < HALF_COLS; ++j) part += v[j];
         sStat[half * TM + row] = part;
     }
     __syncthreads();
     float mean = 0.f;
     if (active) {
-        mean = (sStat[row] + sStat[TM + row]) / float(C);
+        mean = (sStat[row] + sStat[TM + row] + sStat[2 * TM + row] + sStat[3 * TM + row]) / float(C);
         part = 0.f;
 #pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) {
-            const float dlt = (HALF_COLS * half + j < C) ? v[j] - mean : 0.f;
-            part = fmaf(dlt, dlt, part);
+        for (int j = 0; j < HALF_COLS; ++j) { v[j] -= mean; part = fmaf(v[j], v[j], part); }
+        if (partial) {       // the masked columns contributed mean^2 each: take them out again
+            const int nmask = c0 + HALF_COLS - (c0 > C ? c0 : C);
+            part -= float(nmask) * mean * mean;
         }
-        sStat[2 * TM + half * TM + row] = part;
+        sStat[4 * TM + half * TM + row] = part;
     }
     __syncthreads();
     if (active) {
-        const float rstd = rsqrtf((sStat[2 * TM + row] + sStat[3 * TM + row]) / float(C) + kLnEps);
+        const float rstd = rsqrtf((sStat[4 * TM + row] + sStat[5 * TM + row] + sStat[6 * TM + row] + sStat[7 * TM + row]) / float(C) + kLnEps);
 #pragma unroll
-        for (int ch = 0; ch < HALF_CH; ++ch) {
-            float o[8];
+        for (int j = 0; j < HALF_COLS; ++j) v[j] *= rstd;
+        if (partial) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int j = ch * 8 + e, c = HALF_COLS * half + j;
-                o[e] = (c < C) ? (v[j] - mean) * rstd : (c == C ? 1.f : 0.f);
-            }
-            *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
-                make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = (c0 + j == C) ? 1.f : 0.f;
         }
+#pragma unroll
+        for (int ch = 0; ch < HALF_CH; ++ch)
+            *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
+                make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
+                           pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
     }
 }
 
@@ -230,22 +257,25 @@ __device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t i
     }
 }
 
-// u = LeakyReLU(acc + b1f) for my 80 columns -> bf16 tile, column C := 1
+// u = LeakyReLU(acc + b1f) for my 40 columns -> bf16 tile, column C := 1
 __device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, int half, int row, int C, const float* sB1, unsigned char* tile) {
-#pragma unroll 1
-    for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
-        const int j = half * (HALF_COLS / 16) + jj;
-        float v[16];
-        tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+    const int c0 = HALF_COLS * half;
+    const bool has_one = C >= c0 && C < c0 + HALF_COLS;       // warp-uniform
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int n = j * 16 + e;
-            v[e] = (n == C) ? 1.f : lrelu(v[e] + sB1[n]);
+    for (int ch = 0; ch < HALF_CH; ++ch) {
+        const int n0 = c0 + ch * 8;
+        float v[8];
+        tmem_ld8(tmem_addr(tmem, lane_base, n0), v);
+        const float4 b0 = *reinterpret_cast<const float4*>(sB1 + n0), b1 = *reinterpret_cast<const float4*>(sB1 + n0 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float x = v[e] + bb[e]; v[e] = fmaxf(x, kLeakySlope * x); }
+        if (has_one) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (n0 + e == C) v[e] = 1.f;
         }
-        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, 2 * j)) =
+        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
             make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, 2 * j + 1)) =
-            make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
     }
 }
 
@@ -263,8 +293,8 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     unsigned char* sTail = a.prefetch ? sStage + STAGE_BYTES : sA2 + STAGE_BYTES;
     float* sB1 = reinterpret_cast<float*>(sTail);
     float* sBgi = sB1 + CP;
-    float* sStat = sBgi + NC;                    // [4][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 4 * TM);
+    float* sStat = sBgi + NC;                    // [2][NSPLIT][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
     copy_image(sW1, a.ws.w1g, W1_BYTES);
@@ -310,13 +340,12 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
         // gi = acc + (b_ih [+ b_hr, b_hz]) -> bf16 GI tile (coalesced 16-byte chunks); halves split the chunks
         {
             unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-            const int ch0 = half == 0 ? 0 : (NCH + 1) / 2, ch1 = half == 0 ? (NCH + 1) / 2 : NCH;
 #pragma unroll 1
-            for (int ch = ch0; ch < ch1; ++ch) {
+            for (int ch = half; ch < NCH; ch += NSPLIT) {
                 float v[8];
                 tmem_ld8(tmem_addr(tmem, lane_base, 256 + ch * 8), v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += sBgi[ch * 8 + e];
+                const float4 b0 = *reinterpret_cast<const float4*>(sBgi + ch * 8), b1 = *reinterpret_cast<const float4*>(sBgi + ch * 8 + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                 *reinterpret_cast<uint4*>(gout + tile_off(TM, row, ch)) =
                     make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             }
@@ -352,7 +381,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
     if (a.prefetch) sNext += STAGE_BYTES;
     float* sB1 = reinterpret_cast<float*>(sNext);
     float* sStat = sB1 + CP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 4 * TM);  // 0: pre, 1: du, 2: wgrad
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);  // 0: pre, 1: du, 2: wgrad
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
     copy_image(sW1, a.ws.w1g, W1_BYTES);
@@ -387,7 +416,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
         // dGI tile of this item -> scratch (any raw rows there are dead), overlapping the MMA
         {
             const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-            for (int ch = half; ch < NCH; ch += 2)
+            for (int ch = half; ch < NCH; ch += NSPLIT)
                 *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, ch)) = *reinterpret_cast<const uint4*>(gin + tile_off(TM, row, ch));
         }
         mbar_wait(&bars[0], ph0);
@@ -405,17 +434,17 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
                 mma_commit(&bars[2]);
             }
         } else {
-            // LeakyReLU' mask of my 80 columns
-            uint32_t mask[3] = {0u, 0u, 0u};
+            // LeakyReLU' mask of my 40 columns
+            uint32_t mask[2] = {0u, 0u};
 #pragma unroll
-            for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
-                const int j = half * (HALF_COLS / 16) + jj;
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                const int n0 = HALF_COLS * half + ch * 8;
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, n0), v);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int b = jj * 16 + e;
-                    if (v[e] + sB1[j * 16 + e] > 0.f) mask[b >> 5] |= 1u << (b & 31);
+                for (int e = 0; e < 8; ++e) {
+                    const int b = ch * 8 + e;
+                    if (v[e] + sB1[n0 + e] > 0.f) mask[b >> 5] |= 1u << (b & 31);
                 }
             }
             fence_async_smem();
@@ -431,19 +460,17 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
             tc_fence_after_sync();
             // dpre = du * LeakyReLU'(pre) -> bf16 tile over the (dead) dGI tile
 #pragma unroll
-            for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
-                const int j = half * (HALF_COLS / 16) + jj;
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, j * 16), v);
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                const int n0 = HALF_COLS * half + ch * 8;
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, n0), v);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int b = jj * 16 + e;
+                for (int e = 0; e < 8; ++e) {
+                    const int b = ch * 8 + e;
                     v[e] *= ((mask[b >> 5] >> (b & 31)) & 1u) ? 1.f : kLeakySlope;
                 }
-                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, 2 * j)) =
+                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, HALF_CH * half + ch)) =
                     make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, 2 * j + 1)) =
-                    make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
             }
             fence_async_smem();
             tc_fence_before_sync();
@@ -466,13 +493,13 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
         for (int mb = 0; mb < nblk; ++mb) {
             const int orow = mb * 128 + row;
             const bool ok = MODE == 0 ? orow < C : orow < NC;
-            for (int jj = 0; jj < HALF_COLS / 16; ++jj) {
-                const int j = half * (HALF_COLS / 16) + jj;
-                float v[16];
-                tmem_ld16(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + j * 16), v);
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                const int n0 = HALF_COLS * half + ch * 8;
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + n0), v);
                 if (ok) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) atomicAdd(outbuf + size_t(orow) * CP + j * 16 + e, v[e]);
+                    for (int e = 0; e < 8; ++e) atomicAdd(outbuf + size_t(orow) * CP + n0 + e, v[e]);
                 }
             }
         }
