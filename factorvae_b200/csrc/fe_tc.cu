@@ -185,11 +185,17 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
                     issue_row_gemm(tmem, 0, smem_u32(sH), smem_u32(sWhh), NC, NC, HP / 16);
                     mma_commit(bar);
                 }
+            }
+            // my row's gate pre-activations of this step: in flight while the MMA runs
+            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
+            uint4 gq[3 * NB8];
+#pragma unroll
+            for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, c));
+            if (t > 0) {
                 mbar_wait(bar, phase);
                 phase ^= 1;
                 tc_fence_after_sync();
             }
-            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
             unsigned char* hout = reinterpret_cast<unsigned char*>(a.ws.hall) + size_t(st * a.T + t) * HCH * TILE_CH;
 #pragma unroll
             for (int b = 0; b < NB8; ++b) {
@@ -202,9 +208,9 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) ghr[u] = ghz[u] = ghn[u] = 0.f;
                 }
-                unpack8(*reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, 3 * b)), gir);
-                unpack8(*reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, 3 * b + 1)), giz);
-                unpack8(*reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, 3 * b + 2)), gin8);
+                unpack8(gq[3 * b], gir);
+                unpack8(gq[3 * b + 1], giz);
+                unpack8(gq[3 * b + 2], gin8);
                 float hv[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -273,16 +279,22 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
     bool dw_pending = false, dw_started = false;
     for (int64_t st = blockIdx.x; st < a.NT; st += gridDim.x) {
         float dh[8 * NB8];
+        constexpr int MAXHCH = NB8 + 2;          // HP/8 <= NB8 + 2
+        uint4 hq[MAXHCH];
         const int64_t s = st * TM + tid;
 #pragma unroll
         for (int j = 0; j < 8 * NB8; ++j) dh[j] = (s < a.S && j < H) ? a.dE[s * H + j] : 0.f;
         for (int t = a.T - 1; t >= 0; --t) {
             if (dw_pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; dw_pending = false; }   // sHp / sDgh are free again
-            // h_{t-1} operand tile
+            // h_{t-1} operand tile (my row of it was prefetched into registers during the previous step)
             if (t > 0) {
-                const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 1) * HCH * TILE_CH;
-                for (int b = 0; b < HCH; ++b)
-                    *reinterpret_cast<uint4*>(sHp + tile_off(TM, tid, b)) = *reinterpret_cast<const uint4*>(hin + tile_off(TM, tid, b));
+                if (t == a.T - 1) {
+                    const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 1) * HCH * TILE_CH;
+#pragma unroll
+                    for (int b = 0; b < MAXHCH; ++b) if (b < HCH) hq[b] = *reinterpret_cast<const uint4*>(hin + tile_off(TM, tid, b));
+                }
+#pragma unroll
+                for (int b = 0; b < MAXHCH; ++b) if (b < HCH) *reinterpret_cast<uint4*>(sHp + tile_off(TM, tid, b)) = hq[b];
             } else {
                 for (int b = 0; b < HCH; ++b) {
                     uint4 pk = make_uint4(0, 0, 0, 0);
@@ -297,17 +309,26 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
+            if (t > 0 && tid == 0) {
+                tc_fence_after_sync();
+                issue_row_gemm(tmem, 0, smem_u32(sHp), smem_u32(sWhh), NC, NC, HP / 16);
+                mma_commit(&bars[0]);
+            }
+            // global loads in flight while the MMA runs: this step's gate pre-activations, next step's h_{t-2}
+            unsigned char* gio = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
+            uint4 gq[3 * NB8];
+#pragma unroll
+            for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, c));
+            if (t > 1) {
+                const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 2) * HCH * TILE_CH;
+#pragma unroll
+                for (int b = 0; b < MAXHCH; ++b) if (b < HCH) hq[b] = *reinterpret_cast<const uint4*>(hin + tile_off(TM, tid, b));
+            }
             if (t > 0) {
-                if (tid == 0) {
-                    tc_fence_after_sync();
-                    issue_row_gemm(tmem, 0, smem_u32(sHp), smem_u32(sWhh), NC, NC, HP / 16);
-                    mma_commit(&bars[0]);
-                }
                 mbar_wait(&bars[0], ph0);
                 ph0 ^= 1;
                 tc_fence_after_sync();
             }
-            unsigned char* gio = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
 #pragma unroll
             for (int b = 0; b < NB8; ++b) {
                 float ghr[8], ghz[8], ghn[8], gir[8], giz[8], gin8[8], hp[8];
@@ -319,9 +340,9 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) ghr[u] = ghz[u] = ghn[u] = 0.f;
                 }
-                unpack8(*reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, 3 * b)), gir);
-                unpack8(*reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, 3 * b + 1)), giz);
-                unpack8(*reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, 3 * b + 2)), gin8);
+                unpack8(gq[3 * b], gir);
+                unpack8(gq[3 * b + 1], giz);
+                unpack8(gq[3 * b + 2], gin8);
                 unpack8(*reinterpret_cast<const uint4*>(sHp + tile_off(TM, tid, b)), hp);
                 float dar[8], daz[8], dan[8], dnr[8];
 #pragma unroll

@@ -160,6 +160,19 @@ __device__ __forceinline__ void stage_chunk(const HeadsArgs& a, const Smem& s, i
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+// Sweeps use threads as (weight row, stock slice) pairs: with ncol rows and NT threads there are
+// NS = NT / ncol slices, slice s takes stocks s, s+NS, ... of each chunk, and the partial online-softmax
+// states of a row are merged once per date.  Nobody idles at the chunk barriers.
+constexpr int MAXNS = 4;       // cap on slices of the statistics sweep (bounds the merge scratch)
+
+__device__ __forceinline__ void merge_state(float& m, float& l, float m2, float l2, float& sc1, float& sc2) {
+    const float mm = fmaxf(m, m2);
+    sc1 = (m == mm) ? 1.f : expf(m - mm);      // also right when both are -inf / NaN-free by construction
+    sc2 = (m2 == mm) ? 1.f : expf(m2 - mm);
+    l = l * sc1 + l2 * sc2;
+    m = mm;
+}
+
 template <int HP>
 __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
@@ -174,9 +187,14 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     // ---- pass A: online column softmax over the stocks for encoder (M) and attention (K) columns
     const int colA0 = a.predict ? M : 0;
     const int ncolA = a.predict ? K : M + K;
-    for (int cb = 0; cb < ncolA; cb += NT) {
-        const int c = colA0 + cb + tid;
-        const bool act = (cb + tid) < ncolA;
+    const int cpb = ncolA < NT ? ncolA : NT;                     // columns per batch
+    const int NS = (NT / cpb) < MAXNS ? (NT / cpb) : MAXNS;      // stock slices
+    float* scrE = s.F;                                            // [cpb][NS][3]      (m, l, accy)      -- only M of them used
+    float* scrA = s.F + size_t(MAXNS) * 3 * M;                    // [K][NS][HP + 2]   (m, l, accp[HP])
+    for (int cb = 0; cb < ncolA; cb += cpb) {
+        const int cl = tid % cpb, slice = tid / cpb;
+        const int c = colA0 + cb + cl;
+        const bool act = slice < NS && (cb + cl) < ncolA;
         const bool is_att = c >= M;
         const int k = c - M;
         float w[HP];
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
             if (tid < CH) s.ys[tid] = (!a.predict && tid < cn) ? a.y[p0 + i0 + tid] : 0.f;
             __syncthreads();
             if (!act) continue;
-            for (int i = 0; i < cn; ++i) {
+            for (int i = slice; i < cn; i += NS) {
                 const float* er = s.Es + i * HP;
                 float x = dot_row<HP>(w, er) + bias;
                 if (is_att) {
@@ -224,12 +242,46 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
                 }
             }
         }
-        if (act) {
+        // ---- merge the NS partial states of each column
+        __syncthreads();
+        if (act && slice > 0) {
             if (is_att) {
+                float* o = scrA + (size_t(k) * NS + slice) * (HP + 2);
+                o[0] = m; o[1] = l; s.bad[k] = 0;
+#pragma unroll
+                for (int h = 0; h < HP; ++h) o[2 + h] = accp[h];
+            } else {
+                float* o = scrE + (size_t(c) * NS + slice) * 3;
+                o[0] = m; o[1] = l; o[2] = accy;
+            }
+        }
+        if (act && slice == 0 && is_att) s.bad[k] = 0;
+        __syncthreads();
+        if (act && bad) atomicOr(&s.bad[k], 1);
+        __syncthreads();
+        if (act && slice == 0) {
+            for (int q = 1; q < NS; ++q) {
+                float sc1, sc2;
+                if (is_att) {
+                    const float* o = scrA + (size_t(k) * NS + q) * (HP + 2);
+                    if (o[1] > 0.f || o[1] != o[1]) {          // that slice saw at least one stock
+                        merge_state(m, l, o[0], o[1], sc1, sc2);
+#pragma unroll
+                        for (int h = 0; h < HP; ++h) accp[h] = accp[h] * sc1 + o[2 + h] * sc2;
+                    }
+                } else {
+                    const float* o = scrE + (size_t(c) * NS + q) * 3;
+                    if (o[1] > 0.f || o[1] != o[1]) {
+                        merge_state(m, l, o[0], o[1], sc1, sc2);
+                        accy = accy * sc1 + o[2] * sc2;
+                    }
+                }
+            }
+            if (is_att) {
+                const int bd = s.bad[k];
                 a.sv.att_m[size_t(d) * K + k] = m;
                 a.sv.att_l[size_t(d) * K + k] = l;
-                a.sv.bad[size_t(d) * K + k] = bad;
-                s.bad[k] = bad;
+                a.sv.bad[size_t(d) * K + k] = bd;
                 const float inv = 1.f / l;
 #pragma unroll
                 for (int h = 0; h < HP; ++h)
@@ -307,6 +359,9 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     // ---- pass B: decoder per stock (module.py:109-123) + squared error of the sample
     float rec_part = 0.f;
     const int ncolB = K + H;
+    const int cpbB = ncolB < NT ? ncolB : NT;
+    const int NSB = NT / cpbB;
+    constexpr int PPS = NT / CH;                                   // threads per stock in the finishing step
     for (int i0 = 0; i0 < n; i0 += CH) {
         const int cn = min(CH, n - i0);
         __syncthreads();
@@ -316,38 +371,50 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
             s.aux0[tid] = (tid < cn) ? eps_of(a, p0 + i0 + tid) : 0.f;
         }
         __syncthreads();
-        for (int cb = 0; cb < ncolB; cb += NT) {
-            const int cc = cb + tid;
-            if (cc < ncolB) {
+        for (int cb = 0; cb < ncolB; cb += cpbB) {
+            const int cc = cb + tid % cpbB, slice = tid / cpbB;
+            if (cc < ncolB && slice < NSB) {
                 float w[HP];
                 const bool is_beta = cc < K;
                 load_row<HP>(w, is_beta ? a.w.Wb + size_t(cc) * H : a.w.Wa + size_t(cc - K) * H, H, true);
                 const float bias = is_beta ? a.w.bb[cc] : a.w.ba[cc - K];
-                for (int i = 0; i < cn; ++i) s.F[i * FLD + cc] = dot_row<HP>(w, s.Es + i * HP) + bias;
+                for (int i = slice; i < cn; i += NSB) s.F[i * FLD + cc] = dot_row<HP>(w, s.Es + i * HP) + bias;
             }
         }
         __syncthreads();
-        if (tid < cn) {
-            const float* f = s.F + tid * FLD;
-            float amu = a.w.bam[0], asp = a.w.bas[0];
-            for (int j = 0; j < H; ++j) {
-                const float ha = lrelu(f[K + j]);
-                amu = fmaf(a.w.wam[j], ha, amu);
-                asp = fmaf(a.w.was[j], ha, asp);
+        {
+            const int i = tid / PPS, part = tid % PPS;
+            float amu = 0.f, asp = 0.f, mu = 0.f, var = 0.f;
+            if (i < cn) {
+                const float* f = s.F + i * FLD;
+                for (int j = part; j < H; j += PPS) {
+                    const float ha = lrelu(f[K + j]);
+                    amu = fmaf(a.w.wam[j], ha, amu);
+                    asp = fmaf(a.w.was[j], ha, asp);
+                }
+                for (int k = part; k < K; k += PPS) {
+                    const float b = f[k];
+                    mu = fmaf(b, s.muz[k], mu);
+                    var = fmaf(b * b, s.sgz[k] * s.sgz[k], var);
+                }
             }
-            const float asig = softplus(asp);
-            float mu = amu, var = asig * asig;
-            for (int k = 0; k < K; ++k) {
-                const float b = f[k];
-                mu = fmaf(b, s.muz[k], mu);
-                var = fmaf(b * b, s.sgz[k] * s.sgz[k], var);
+#pragma unroll
+            for (int o = PPS / 2; o > 0; o >>= 1) {
+                amu += __shfl_xor_sync(0xffffffffu, amu, o);
+                asp += __shfl_xor_sync(0xffffffffu, asp, o);
+                mu += __shfl_xor_sync(0xffffffffu, mu, o);
+                var += __shfl_xor_sync(0xffffffffu, var, o);
             }
-            const float sy = sqrtf(var + 1e-6f);
-            const float yh = fmaf(s.aux0[tid], sy, mu);
-            const int u = p0 + i0 + tid;
-            a.out.yhat[u] = yh; a.out.mu_y[u] = mu; a.out.sigma_y[u] = sy;
-            const float dlt = yh - s.ys[tid];
-            rec_part = fmaf(dlt, dlt, rec_part);
+            if (i < cn && part == 0) {
+                const float asig = softplus(asp + a.w.bas[0]);
+                mu += amu + a.w.bam[0];
+                const float sy = sqrtf(var + asig * asig + 1e-6f);
+                const float yh = fmaf(s.aux0[i], sy, mu);
+                const int u = p0 + i0 + i;
+                a.out.yhat[u] = yh; a.out.mu_y[u] = mu; a.out.sigma_y[u] = sy;
+                const float dlt = yh - s.ys[i];
+                rec_part = fmaf(dlt, dlt, rec_part);
+            }
         }
     }
     if (a.predict) return;
@@ -377,7 +444,8 @@ __device__ __forceinline__ ColRef col_ref(const HeadsArgs& a, int c) {
     return r;
 }
 
-template <int HP, int NB>
+// WSM: the stacked weight rows [Wp; G; Wb; Wa] are staged in shared memory for the dE sweep
+template <int HP, int NB, bool WSM>
 __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, float* __restrict__ dE) {
     extern __shared__ __align__(16) float smem_raw[];
     const int H = a.H, K = a.K, M = a.M;
@@ -413,7 +481,8 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
     float* dps = sm;           sm += K * H;  // dp_k
     float* tmpKH = sm;         sm += K * H;  // dhm_pre, then dctx
     float* Aatt = sm;          sm += CH * (K | 1);
-    float* Z = sm;                            // CH * ZLD
+    float* Z = sm;             sm += CH * ZLD;
+    float* Wc = sm;                           // WSM: [NF][HP] stacked weight rows (G rows pre-divided? no: plain)
     const int ALD = K | 1;
 
     const float tau = sqrtf(float(H) + 1e-6f);
@@ -432,40 +501,58 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         attm[k] = a.sv.att_m[size_t(d) * K + k];
         attl[k] = a.sv.att_l[size_t(d) * K + k];
         bad[k] = a.sv.bad[size_t(d) * K + k];
+        dmupost[k] = 0.f; dprepost[k] = 0.f;
     }
     for (int idx = tid; idx < K * H; idx += NT) pooled[idx] = a.sv.pooled[size_t(d) * K * H + idx];
+    if (WSM) {
+        for (int idx = tid; idx < NF * HP; idx += NT) {
+            const int c = idx / HP, h = idx % HP;
+            float v = 0.f;
+            if (h < H) {
+                if (c < M) v = a.w.Wp[size_t(c) * H + h];
+                else if (c < M + K) v = a.sv.G[size_t(c - M) * H + h];
+                else if (c < M + 2 * K) v = a.w.Wb[size_t(c - M - K) * H + h];
+                else v = a.w.Wa[size_t(c - M - 2 * K) * H + h];
+            }
+            Wc[idx] = v;
+        }
+    }
     __syncthreads();
 
     // ---- pass C1: d mu_z[k] = sum_i beta_ik dmu_y_i ; d sigma_z[k] = 2 sigma_z[k] sum_i beta_ik^2 dv_i
-    for (int kb = 0; kb < K; kb += NT) {
-        const int k = kb + tid;
-        const bool act = k < K;
-        float w[HP];
-        load_row<HP>(w, a.w.Wb + size_t(act ? k : 0) * H, H, act);
-        const float bias = act ? a.w.bb[k] : 0.f;
-        float acc1 = 0.f, acc2 = 0.f;
-        for (int i0 = 0; i0 < n; i0 += CH) {
-            const int cn = min(CH, n - i0);
-            __syncthreads();
-            stage_chunk<HP>(a, Smem{Es}, p0, i0, cn);
-            if (tid < CH) {
-                float v1 = 0.f, v2 = 0.f;
-                if (tid < cn) {
-                    const int u = p0 + i0 + tid;
-                    v1 = coefN * (a.out.yhat[u] - a.y[u]);
-                    v2 = v1 * eps_of(a, u) / (2.f * a.out.sigma_y[u]);
+    {
+        const int cpb = K < NT ? K : NT;
+        const int NS1 = NT / cpb;
+        for (int kb = 0; kb < K; kb += cpb) {
+            const int k = kb + tid % cpb, slice = tid / cpb;
+            const bool act = k < K && slice < NS1;
+            float w[HP];
+            load_row<HP>(w, a.w.Wb + size_t(act ? k : 0) * H, H, act);
+            const float bias = act ? a.w.bb[k] : 0.f;
+            float acc1 = 0.f, acc2 = 0.f;
+            for (int i0 = 0; i0 < n; i0 += CH) {
+                const int cn = min(CH, n - i0);
+                __syncthreads();
+                stage_chunk<HP>(a, Smem{Es}, p0, i0, cn);
+                if (tid < CH) {
+                    float v1 = 0.f, v2 = 0.f;
+                    if (tid < cn) {
+                        const int u = p0 + i0 + tid;
+                        v1 = coefN * (a.out.yhat[u] - a.y[u]);
+                        v2 = v1 * eps_of(a, u) / (2.f * a.out.sigma_y[u]);
+                    }
+                    dmy[tid] = v1; dvv[tid] = v2;
                 }
-                dmy[tid] = v1; dvv[tid] = v2;
+                __syncthreads();
+                if (act)
+                    for (int i = slice; i < cn; i += NS1) {
+                        const float b = dot_row<HP>(w, Es + i * HP) + bias;
+                        acc1 = fmaf(b, dmy[i], acc1);
+                        acc2 = fmaf(b * b, dvv[i], acc2);
+                    }
             }
-            __syncthreads();
-            if (act)
-                for (int i = 0; i < cn; ++i) {
-                    const float b = dot_row<HP>(w, Es + i * HP) + bias;
-                    acc1 = fmaf(b, dmy[i], acc1);
-                    acc2 = fmaf(b * b, dvv[i], acc2);
-                }
+            if (act) { atomicAdd(&dmupost[k], acc1); atomicAdd(&dprepost[k], 2.f * sgz[k] * acc2); }   // staged: d mu_z, d sigma_z
         }
-        if (act) { dmupost[k] = acc1; dprepost[k] = 2.f * sgz[k] * acc2; }   // staged: d mu_z, d sigma_z
     }
     __syncthreads();
 
@@ -563,9 +650,17 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
     __syncthreads();
 
     // ---- pass C2: Z sweep -> weight gradients (registers) and dE
+    // thread = (weight row c, stock slice): rows per batch cpb2, NS2 slices, NB batches of rows
+    const int cpb2 = NF < NT ? NF : NT;
+    const int NS2 = NT / cpb2;
+    const int mycl = tid % cpb2, myslice = tid / cpb2;
+    const bool slice_ok = myslice < NS2;
+    const int cpbA = H < NT ? H : NT;                     // alpha rows in S1c
+    const int NSA = NT / cpbA;
+    constexpr int PPS = NT / CH;
     float acc[NB][HP];
     float accb[NB];
-    float acc_wam = 0.f, acc_was = 0.f;       // alpha-column threads only
+    float acc_wam = 0.f, acc_was = 0.f;       // S1c threads only
     float sum_damu = 0.f, sum_dasp = 0.f;     // per-stock threads
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
@@ -591,24 +686,24 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         // S1: F = e . w_c (+bias) and its transform into the backward coefficient Z[i][c]
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            const int c = b * NT + tid;
-            if (c < NF) {
+            const int c = b * cpb2 + mycl;
+            if (c < NF && slice_ok) {
                 const ColRef cr = col_ref(a, c);
                 float w[HP];
                 if (cr.kind == 1 && bad[cr.idx]) {
-                    for (int i = 0; i < cn; ++i) { Z[i * ZLD + c] = 0.f; Aatt[i * ALD + cr.idx] = 0.f; }
+                    for (int i = myslice; i < cn; i += NS2) { Z[i * ZLD + c] = 0.f; Aatt[i * ALD + cr.idx] = 0.f; }
                 } else {
                     load_row<HP>(w, cr.w, H, true);
                     if (cr.kind == 0) {                         // encoder: dlogit = w_ij dyp_j (y_i - yp_j)
                         const float mj = encm[c], lj = encl[c], dj = dyp[c], ypj = yp[c];
-                        for (int i = 0; i < cn; ++i) {
+                        for (int i = myslice; i < cn; i += NS2) {
                             const float x = dot_row<HP>(w, Es + i * HP) + cr.bias;
                             Z[i * ZLD + c] = expf(x - mj) / lj * dj * (ys[i] - ypj);
                         }
                     } else if (cr.kind == 1) {                  // attention: a_ik now, ds_ik after the dp sweep
                         const int k = cr.idx;
                         const float mk = attm[k], lk = attl[k];
-                        for (int i = 0; i < cn; ++i) {
+                        for (int i = myslice; i < cn; i += NS2) {
                             float x = (dot_row<HP>(w, Es + i * HP) + cr.bias) / tau;
                             const float kf = keep_factor(a, p0 + i0 + i, k);
                             x = x * kf;
@@ -619,46 +714,53 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                         }
                         load_row<HP>(w, dps + k * H, H, true);   // second sweep with dp_k
                         const float pk = pdp[k];
-                        for (int i = 0; i < cn; ++i) {
+                        for (int i = myslice; i < cn; i += NS2) {
                             const float dr = Aatt[i * ALD + k] * (dot_row<HP>(w, Es + i * HP) - pk);
                             Z[i * ZLD + c] *= dr;
                         }
                     } else if (cr.kind == 2) {                  // beta: mu_z dmu_y + 2 beta sigma_z^2 dv
                         const float mz = muz[cr.idx], sz2 = sgz[cr.idx] * sgz[cr.idx];
-                        for (int i = 0; i < cn; ++i) {
+                        for (int i = myslice; i < cn; i += NS2) {
                             const float bt = dot_row<HP>(w, Es + i * HP) + cr.bias;
                             Z[i * ZLD + c] = mz * dmy[i] + 2.f * bt * sz2 * dvv[i];
                         }
                     } else {                                    // alpha hidden: keep pre-activation for S1b/S1c
-                        for (int i = 0; i < cn; ++i) Z[i * ZLD + c] = dot_row<HP>(w, Es + i * HP) + cr.bias;
+                        for (int i = myslice; i < cn; i += NS2) Z[i * ZLD + c] = dot_row<HP>(w, Es + i * HP) + cr.bias;
                     }
                 }
             }
         }
         __syncthreads();
-        // S1b: per stock, alpha scalars: asig = softplus(was . lrelu(ha_pre) + bas)
-        if (tid < CH) {
-            float v1 = 0.f, v2 = 0.f;
-            if (tid < cn) {
-                const float* zr = Z + tid * ZLD + (M + 2 * K);
-                float asp = a.w.bas[0];
-                for (int j = 0; j < H; ++j) asp = fmaf(a.w.was[j], lrelu(zr[j]), asp);
-                const float asig = softplus(asp);
-                v1 = dmy[tid];                                     // d alpha_mu
-                v2 = 2.f * asig * dvv[tid] * softplus_grad(asp);   // d (pre-softplus alpha_sigma)
-                sum_damu += v1; sum_dasp += v2;
+        // S1b: per stock, alpha scalars: asig = softplus(was . lrelu(ha_pre) + bas); PPS threads per stock
+        {
+            const int i = tid / PPS, part = tid % PPS;
+            float asp = 0.f;
+            if (i < cn) {
+                const float* zr = Z + i * ZLD + (M + 2 * K);
+                for (int j = part; j < H; j += PPS) asp = fmaf(a.w.was[j], lrelu(zr[j]), asp);
             }
-            damu[tid] = v1; dasp[tid] = v2;
+#pragma unroll
+            for (int o = PPS / 2; o > 0; o >>= 1) asp += __shfl_xor_sync(0xffffffffu, asp, o);
+            if (part == 0) {
+                float v1 = 0.f, v2 = 0.f;
+                if (i < cn) {
+                    asp += a.w.bas[0];
+                    const float asig = softplus(asp);
+                    v1 = dmy[i];                                     // d alpha_mu
+                    v2 = 2.f * asig * dvv[i] * softplus_grad(asp);   // d (pre-softplus alpha_sigma)
+                    sum_damu += v1; sum_dasp += v2;
+                }
+                damu[i] = v1; dasp[i] = v2;
+            }
         }
         __syncthreads();
-        // S1c: alpha columns: mu/sigma layer weight grads, then Z := d ha_pre
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const int c = b * NT + tid;
-            if (c >= M + 2 * K && c < NF) {
-                const int j = c - (M + 2 * K);
+        // S1c: alpha rows: mu/sigma layer weight grads, then Z := d ha_pre      thread = (alpha row j, slice)
+        for (int jb = 0; jb < H; jb += cpbA) {
+            const int j = jb + tid % cpbA, sl = tid / cpbA;
+            if (j < H && sl < NSA) {
+                const int c = M + 2 * K + j;
                 const float wm = a.w.wam[j], ws = a.w.was[j];
-                for (int i = 0; i < cn; ++i) {
+                for (int i = sl; i < cn; i += NSA) {
                     const float pre = Z[i * ZLD + c];
                     const float ha = lrelu(pre);
                     acc_wam = fmaf(damu[i], ha, acc_wam);
@@ -671,9 +773,9 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         // S2: weight-row gradients  dW_c += sum_i Z[i][c] e_i ; bias grads
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            const int c = b * NT + tid;
-            if (c < NF) {
-                for (int i = 0; i < cn; ++i) {
+            const int c = b * cpb2 + mycl;
+            if (c < NF && slice_ok) {
+                for (int i = myslice; i < cn; i += NS2) {
                     const float z = Z[i * ZLD + c];
                     accb[b] += z;
                     const float4* e4 = reinterpret_cast<const float4*>(Es + i * HP);
@@ -688,9 +790,9 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                 }
             }
         }
-        // S3: dE[i][:] = sum_c Z[i][c] Wcat[c][:] + sum_k a_ik dp_k    (thread: stock i, quarter of H)
+        // S3: dE[i][:] = sum_c Z[i][c] Wcat[c][:] + sum_k a_ik dp_k    (thread: stock i, part of H)
         {
-            constexpr int HQ = HP / 4;
+            constexpr int HQ = HP / PPS;
             const int i = tid % CH, hq = tid / CH;
             if (i < cn) {
                 float o[HQ];
@@ -699,16 +801,17 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                 const float* zr = Z + i * ZLD;
                 for (int c = 0; c < NF; ++c) {
                     const float z = zr[c];
-                    const float* wr;
-                    if (c < M) wr = a.w.Wp + size_t(c) * H;
-                    else if (c < M + K) wr = a.sv.G + size_t(c - M) * H;
-                    else if (c < M + 2 * K) wr = a.w.Wb + size_t(c - M - K) * H;
-                    else wr = a.w.Wa + size_t(c - M - 2 * K) * H;
                     if (z != 0.f) {                       // also keeps 0*inf of a tripped head out
+                        const float* wr;
+                        if (WSM) wr = Wc + c * HP;
+                        else if (c < M) wr = a.w.Wp + size_t(c) * H;
+                        else if (c < M + K) wr = a.sv.G + size_t(c - M) * H;
+                        else if (c < M + 2 * K) wr = a.w.Wb + size_t(c - M - K) * H;
+                        else wr = a.w.Wa + size_t(c - M - 2 * K) * H;
 #pragma unroll
                         for (int t = 0; t < HQ; ++t) {
                             const int h = hq * HQ + t;
-                            if (h < H) o[t] = fmaf(z, wr[h], o[t]);
+                            if (WSM || h < H) o[t] = fmaf(z, wr[h], o[t]);
                         }
                     }
                 }
@@ -729,11 +832,11 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
             }
         }
     }
-    // ---- flush the register accumulators (one red.global.add per parameter per CTA)
+    // ---- flush the register accumulators (one red.global.add per parameter per (CTA, slice))
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const int c = b * NT + tid;
-        if (c < NF) {
+        const int c = b * cpb2 + mycl;
+        if (c < NF && slice_ok) {
             float* gw; float* gb;
             if (c < M) { gw = g.Wp + size_t(c) * H; gb = g.bp + c; }
             else if (c < M + K) { gw = a.sv.dG + size_t(c - M) * H; gb = a.sv.dc + (c - M); }
@@ -745,12 +848,11 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                 for (int h = 0; h < HP; ++h) if (h < H) atomicAdd(gw + h, acc[b][h]);
                 atomicAdd(gb, accb[b]);
             }
-            if (c >= M + 2 * K) {
-                const int j = c - (M + 2 * K);
-                atomicAdd(g.wam + j, acc_wam);
-                atomicAdd(g.was + j, acc_was);
-            }
         }
+    }
+    for (int jb = 0; jb < H; jb += cpbA) {
+        const int j = jb + tid % cpbA, sl = tid / cpbA;
+        if (j < H && sl < NSA && jb == 0) { atomicAdd(g.wam + j, acc_wam); atomicAdd(g.was + j, acc_was); }
     }
     sum_damu = block_sum(sum_damu, red);
     sum_dasp = block_sum(sum_dasp, red);
@@ -761,11 +863,15 @@ size_t fwd_smem_bytes(int HP, int H, int K, int M) {
     size_t f = size_t(CH) * HP + 3 * CH + 32 + M + 5 * size_t(K) + 2 * size_t(K) * H;
     size_t fl = size_t(CH) * ((K + H) | 1);
     size_t hm = size_t(K) * H;
-    return (f + (fl > hm ? fl : hm)) * sizeof(float);
+    size_t mg = size_t(MAXNS) * (3 * size_t(M) + size_t(K) * (HP + 2));     // merge scratch of the statistics sweep
+    size_t mx = fl > hm ? fl : hm;
+    if (mg > mx) mx = mg;
+    return (f + mx) * sizeof(float);
 }
-size_t bwd_smem_bytes(int HP, int H, int K, int M) {
+size_t bwd_smem_bytes(int HP, int H, int K, int M, bool wsm) {
     size_t f = size_t(CH) * HP + 5 * CH + 32 + 4 * size_t(M) + 10 * size_t(K) + 3 * size_t(K) * H
              + size_t(CH) * (K | 1) + size_t(CH) * ((M + 2 * K + H) | 1);
+    if (wsm) f += size_t(M + 2 * K + H) * HP;
     return f * sizeof(float);
 }
 
@@ -812,17 +918,19 @@ int heads_backward(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t 
     const int NF = a.M + 2 * a.K + a.H;
     const int NB = (NF + NT - 1) / NT;
     if (NB > 3) return FVAE_ERR_LIMIT;
-    const size_t smem = bwd_smem_bytes(HP, a.H, a.K, a.M);
+    const bool wsm = HP == 32 && bwd_smem_bytes(HP, a.H, a.K, a.M, true) <= 110 * 1024;   // keep two CTAs per SM
+    const size_t smem = bwd_smem_bytes(HP, a.H, a.K, a.M, wsm);
     int rc;
-#define FVAE_LAUNCH_BWD(HPV, NBV)                                                      \
-    do {                                                                               \
-        if ((rc = set_smem(heads_bwd_kernel<HPV, NBV>, smem)) != 0) return rc;         \
-        heads_bwd_kernel<HPV, NBV><<<a.B, NT, smem, stream>>>(a, g, dE); count_launch();               \
+#define FVAE_LAUNCH_BWD(HPV, NBV, WSMV)                                                      \
+    do {                                                                                     \
+        if ((rc = set_smem(heads_bwd_kernel<HPV, NBV, WSMV>, smem)) != 0) return rc;         \
+        heads_bwd_kernel<HPV, NBV, WSMV><<<a.B, NT, smem, stream>>>(a, g, dE); count_launch(); \
     } while (0)
     if (HP == 32) {
-        if (NB == 1) FVAE_LAUNCH_BWD(32, 1); else if (NB == 2) FVAE_LAUNCH_BWD(32, 2); else FVAE_LAUNCH_BWD(32, 3);
+        if (wsm) { if (NB == 1) FVAE_LAUNCH_BWD(32, 1, true); else if (NB == 2) FVAE_LAUNCH_BWD(32, 2, true); else FVAE_LAUNCH_BWD(32, 3, true); }
+        else { if (NB == 1) FVAE_LAUNCH_BWD(32, 1, false); else if (NB == 2) FVAE_LAUNCH_BWD(32, 2, false); else FVAE_LAUNCH_BWD(32, 3, false); }
     } else {
-        if (NB == 1) FVAE_LAUNCH_BWD(64, 1); else if (NB == 2) FVAE_LAUNCH_BWD(64, 2); else return FVAE_ERR_LIMIT;
+        if (NB == 1) FVAE_LAUNCH_BWD(64, 1, false); else if (NB == 2) FVAE_LAUNCH_BWD(64, 2, false); else return FVAE_ERR_LIMIT;
     }
 #undef FVAE_LAUNCH_BWD
     return int(cudaGetLastError());
