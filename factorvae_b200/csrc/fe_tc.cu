@@ -101,6 +101,7 @@ __global__ void tc_prep_kernel(PrepArgs a) {
     // W1g[n][k] = W1[n][k] * gamma[k]
     for (int idx = tid; idx < CP * CP; idx += nth) {
         const int n = idx / CP, k = idx % CP;
+        if (k == C) continue;                    // column C carries the folded bias (written below by another thread)
         put_img(a.ws.w1g, CP, n, k, (n < C && k < C) ? a.W1[n * C + k] * a.ln_w[k] : 0.f);
     }
     // W_ih (rows permuted) and its transpose
@@ -109,7 +110,7 @@ __global__ void tc_prep_kernel(PrepArgs a) {
         int gate, j;
         const bool ok = unperm_col(col, H, gate, j) && k < C;
         const float v = ok ? a.Wih[(gate * H + j) * C + k] : 0.f;
-        put_img(a.ws.wih, NC, col, k, v);       // B[n=col][k]
+        if (k != C) put_img(a.ws.wih, NC, col, k, v);       // B[n=col][k]; column C carries the folded bias
         put_img(a.ws.wihT, CP, k, col, v);      // B[n=k(feature)][k=col]
     }
     // W_hh (rows permuted) and its transpose
@@ -121,6 +122,7 @@ __global__ void tc_prep_kernel(PrepArgs a) {
         put_img(a.ws.whh, NC, col, k, v);
         put_img(a.ws.whhT, HP, k, col, v);
     }
+    // biases ride in column C of the images (column C of the xhat / u operand tiles is the constant 1)
     for (int n = tid; n < CP; n += nth) {
         float v = 0.f;
         if (n < C) {
@@ -128,12 +130,14 @@ __global__ void tc_prep_kernel(PrepArgs a) {
             for (int k = 0; k < C; ++k) v = fmaf(a.W1[n * C + k], a.ln_b[k], v);
         }
         a.ws.b1f[n] = v;
+        put_img(a.ws.w1g, CP, n, C, v);
     }
     for (int col = tid; col < NC; col += nth) {
         int gate, j;
         float v = 0.f;
         if (unperm_col(col, H, gate, j)) v = a.bih[gate * H + j] + (gate < 2 ? a.bhh[gate * H + j] : 0.f);
         a.ws.bgi[col] = v;
+        put_img(a.ws.wih, NC, col, C, v);
     }
     for (int j = tid; j < HP; j += nth) a.ws.bhn[j] = j < H ? a.bhh[2 * H + j] : 0.f;
 }
@@ -580,8 +584,14 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     if (bf) {
         a.prefetch = pf0;
         if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 0>, grid, smem0, st, a)) != 0) return rc;
-        a.prefetch = pf1;
-        if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 1>, grid, smem1, st, a)) != 0) return rc;
+        const size_t pipe = W1_BYTES + 2 * A_BYTES + 2 * size_t(NC / 8) * TILE_CH + STAGE_BYTES + tail;
+        if (pipe <= kMaxSmem) {
+            a.prefetch = 1;
+            if ((rc = launch_smem(tc_front_bwd_wih_pipe_kernel<__nv_bfloat16>, grid, pipe, st, a)) != 0) return rc;
+        } else {
+            a.prefetch = pf1;
+            if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 1>, grid, smem1, st, a)) != 0) return rc;
+        }
     } else {
         a.prefetch = 0;
         if ((rc = launch_smem(tc_front_bwd_kernel<float, 0>, grid, smem0, st, a)) != 0) return rc;

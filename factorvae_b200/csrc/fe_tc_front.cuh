@@ -58,10 +58,9 @@ constexpr uint32_t STAGE_BYTES = 43008;      // 128 slots x 336 B (bf16 rows) >=
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <typename XT>
 __device__ __forceinline__ uint32_t slot_bytes(int C) {
     uint32_t s = ((uint32_t(C) * sizeof(XT) + 15u) & ~15u) + 16u;
@@ -182,9 +181,10 @@ __device__ __forceinline__ void fetch_half(const float*, const unsigned char* sl
     }
 }
 
-// LayerNorm of the rows staged for pass `r0` (statistics in fp32 over exactly C features) -> xhat bf16 tile,
-// column C := 1.  Called by all threads (two block barriers inside).  Only the thread whose 40 columns
-// straddle C pays for masking.
+// LayerNorm of the rows staged for pass `r0` -> xhat bf16 tile, column C := 1.  Called by all threads (one block
+// barrier inside).  Statistics are fp32 sums of x and x^2 over exactly C features (var = E[x^2] - mean^2: the
+// cancellation only bites when |mean| >> std, where bf16 operands have already lost the signal; the fp32 mode
+// keeps the two-pass form).  Only the thread whose 40 columns straddle C pays for masking.
 template <typename XT>
 __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, int t, const unsigned char* stage, int r0,
                                                unsigned char* tile, float* sStat) {
@@ -192,41 +192,44 @@ __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, in
     const bool active = row >= r0 && row < r0 + Rows<XT>::PER_PASS;
     const int c0 = HALF_COLS * half;
     const bool partial = c0 + HALF_COLS > C;            // warp-uniform
+    const bool tail_only = C >= c0 + HALF_COLS - 8;     // only my last chunk holds columns >= C
     float v[HALF_COLS];
-    float part = 0.f;
     if (active) {
         const int64_t s = st * TM + row;
         const uint32_t off = s < a.S ? uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u) : 0u;
         fetch_half(static_cast<const XT*>(nullptr), stage + size_t(row - r0) * slot_bytes<XT>(C), off, half, v);
         if (partial) {
+            if (tail_only) {
 #pragma unroll
-            for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = 0.f;
+                for (int j = HALF_COLS - 8; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = 0.f;
+            }
         }
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) part += v[j];
-        sStat[half * TM + row] = part;
-    }
-    __syncthreads();
-    float mean = 0.f;
-    if (active) {
-        mean = (sStat[row] + sStat[TM + row] + sStat[2 * TM + row] + sStat[3 * TM + row]) / float(C);
-        part = 0.f;
-#pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) { v[j] -= mean; part = fmaf(v[j], v[j], part); }
-        if (partial) {       // the masked columns contributed mean^2 each: take them out again
-            const int nmask = c0 + HALF_COLS - (c0 > C ? c0 : C);
-            part -= float(nmask) * mean * mean;
-        }
-        sStat[4 * TM + half * TM + row] = part;
+        for (int j = 0; j < HALF_COLS; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+        sStat[half * TM + row] = s1;
+        sStat[NSPLIT * TM + half * TM + row] = s2;
     }
     __syncthreads();
     if (active) {
-        const float rstd = rsqrtf((sStat[4 * TM + row] + sStat[5 * TM + row] + sStat[6 * TM + row] + sStat[7 * TM + row]) / float(C) + kLnEps);
+        const float inv_c = 1.f / float(C);
+        const float mean = (sStat[row] + sStat[TM + row] + sStat[2 * TM + row] + sStat[3 * TM + row]) * inv_c;
+        const float ex2 = (sStat[4 * TM + row] + sStat[5 * TM + row] + sStat[6 * TM + row] + sStat[7 * TM + row]) * inv_c;
+        const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + kLnEps);
+        const float shift = -mean * rstd;
 #pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) v[j] *= rstd;
+        for (int j = 0; j < HALF_COLS; ++j) v[j] = fmaf(v[j], rstd, shift);
         if (partial) {
+            if (tail_only) {
 #pragma unroll
-            for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = (c0 + j == C) ? 1.f : 0.f;
+                for (int j = HALF_COLS - 8; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = (c0 + j == C) ? 1.f : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = (c0 + j == C) ? 1.f : 0.f;
+            }
         }
 #pragma unroll
         for (int ch = 0; ch < HALF_CH; ++ch)
@@ -236,46 +239,58 @@ __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, in
     }
 }
 
-// all loads of one item (bf16: one pass; fp32: the given pass)
+// all loads of one item (bf16: one pass; fp32: the given pass), committed as ONE cp.async group
 template <typename XT>
 __device__ __forceinline__ void issue_item_loads(const ItemArgs& a, int64_t item, unsigned char* stage, int r0) {
     load_rows_async<XT>(a, item / a.T, int(item % a.T), stage, r0);
+    cp_async_commit();
+}
+// my share of a [NCH x 128 x 16 B] operand tile in HBM -> shared memory, as one cp.async group
+__device__ __forceinline__ void issue_tile_load(unsigned char* dst, const unsigned char* src, int nch, int row, int part) {
+    for (int ch = part; ch < nch; ch += NSPLIT) cp_async16(smem_u32(dst + tile_off(TM, row, ch)), src + tile_off(TM, row, ch));
+    cp_async_commit();
 }
 
-// stage (unless already prefetched) + LayerNorm of one item -> xhat tile
+// stage (unless already issued) + LayerNorm of one item -> xhat tile.  allow_pending: one younger cp.async
+// group (a tile prefetch issued after the rows) may still be in flight.
 template <typename XT>
 __device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t item, unsigned char* stage, unsigned char* tile,
-                                                    float* sStat, bool already_issued) {
+                                                    float* sStat, bool already_issued, bool allow_pending = false) {
     const int64_t st = item / a.T;
     const int t = int(item % a.T);
     for (int r0 = 0; r0 < TM; r0 += Rows<XT>::PER_PASS) {
         if (r0 > 0) __syncthreads();
-        if (!(already_issued && r0 == 0)) load_rows_async<XT>(a, st, t, stage, r0);
-        cp_async_wait_all();
+        if (!(already_issued && r0 == 0)) { load_rows_async<XT>(a, st, t, stage, r0); cp_async_commit(); }
+        if (allow_pending && r0 == 0 && already_issued) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
         layernorm_pass<XT>(a, st, t, stage, r0, tile, sStat);
     }
 }
 
-// u = LeakyReLU(acc + b1f) for my 40 columns -> bf16 tile, column C := 1
-__device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, int half, int row, int C, const float* sB1, unsigned char* tile) {
+// u = LeakyReLU(acc) for my 40 columns -> bf16 tile, column C := 1.  The bias b1f is already in acc: column C of
+// the xhat tile is the constant 1 and column C of the W1g image holds b1f.  max(x, 0.01 x) runs on packed bf16x2.
+__device__ __forceinline__ uint32_t lrelu_pack(float lo, float hi) {
+    const __nv_bfloat162 x = __floats2bfloat162_rn(lo, hi);
+    const __nv_bfloat162 y = __hmax2(x, __hmul2(x, __floats2bfloat162_rn(kLeakySlope, kLeakySlope)));
+    return *reinterpret_cast<const uint32_t*>(&y);
+}
+__device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, int half, int row, int C, unsigned char* tile) {
     const int c0 = HALF_COLS * half;
-    const bool has_one = C >= c0 && C < c0 + HALF_COLS;       // warp-uniform
+    const int one_ch = (C >= c0 && C < c0 + HALF_COLS) ? (C - c0) >> 3 : -1;       // warp-uniform
 #pragma unroll
     for (int ch = 0; ch < HALF_CH; ++ch) {
-        const int n0 = c0 + ch * 8;
         float v[8];
-        tmem_ld8(tmem_addr(tmem, lane_base, n0), v);
-        const float4 b0 = *reinterpret_cast<const float4*>(sB1 + n0), b1 = *reinterpret_cast<const float4*>(sB1 + n0 + 4);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { const float x = v[e] + bb[e]; v[e] = fmaxf(x, kLeakySlope * x); }
-        if (has_one) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) if (n0 + e == C) v[e] = 1.f;
+        tmem_ld8(tmem_addr(tmem, lane_base, c0 + ch * 8), v);
+        uint32_t w0 = lrelu_pack(v[0], v[1]), w1 = lrelu_pack(v[2], v[3]), w2 = lrelu_pack(v[4], v[5]), w3 = lrelu_pack(v[6], v[7]);
+        if (ch == one_ch) {
+            const int e = (C - c0) & 7, q = e >> 1;
+            const uint32_t one = 0x3F80u << (16 * (e & 1)), keep = 0xFFFFu << (16 * ((e & 1) ^ 1));
+            if (q == 0) w0 = (w0 & keep) | one;
+            else if (q == 1) w1 = (w1 & keep) | one;
+            else if (q == 2) w2 = (w2 & keep) | one;
+            else w3 = (w3 & keep) | one;
         }
-        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
-            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) = make_uint4(w0, w1, w2, w3);
     }
 }
 
@@ -311,47 +326,88 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     const uint32_t lane_base = uint32_t(warp & 3) * 32u;
     const int64_t nitems = a.NT * a.T;
     const bool prefetch = a.prefetch != 0 && sizeof(XT) == 2;
-    uint32_t phase = 0;
-    if (prefetch && int64_t(blockIdx.x) < nitems) issue_item_loads<XT>(a, blockIdx.x, sStage, 0);
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, phase ^= 1) {
-        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, prefetch);
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
+    // gi = acc + (b_ih [+ b_hr, b_hz]) -> bf16 GI tile (coalesced 16-byte chunks); the column parts split the chunks
+    auto epilogue_gi = [&](int64_t item) {
+        unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
+#pragma unroll 1
+        for (int ch = half; ch < NCH; ch += NSPLIT) {
+            float v[8];
+            tmem_ld8(tmem_addr(tmem, lane_base, 256 + ch * 8), v);       // bias included: u tile column C = 1, image column C = bias
+            *reinterpret_cast<uint4*>(gout + tile_off(TM, row, ch)) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+    };
+    auto issue_gemm1 = [&]() {
         if (tid == 0) {
             tc_fence_after_sync();
             issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);
             mma_commit(&bars[0]);
         }
-        if (prefetch && item + gridDim.x < nitems) issue_item_loads<XT>(a, item + gridDim.x, sStage, 0);   // stage is free
-        mbar_wait(&bars[0], phase);
-        tc_fence_after_sync();
-        epilogue_u(tmem, lane_base, half, row, C, sB1, sA2);
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
+    };
+    auto issue_gemm2 = [&]() {
         if (tid == 0) {
             tc_fence_after_sync();
             issue_row_gemm(tmem, 256, smem_u32(sA2), smem_u32(sWih), NC, NC, KCH / 2);
             mma_commit(&bars[1]);
         }
-        mbar_wait(&bars[1], phase);
-        tc_fence_after_sync();
-        // gi = acc + (b_ih [+ b_hr, b_hz]) -> bf16 GI tile (coalesced 16-byte chunks); halves split the chunks
-        {
-            unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-#pragma unroll 1
-            for (int ch = half; ch < NCH; ch += NSPLIT) {
-                float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, 256 + ch * 8), v);
-                const float4 b0 = *reinterpret_cast<const float4*>(sBgi + ch * 8), b1 = *reinterpret_cast<const float4*>(sBgi + ch * 8 + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                *reinterpret_cast<uint4*>(gout + tile_off(TM, row, ch)) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
+    };
+    const int64_t G = gridDim.x;
+    uint32_t phase = 0;
+    if (prefetch) {
+        // Software pipeline over items (dedicated raw-row stage):  GEMM2(k) runs under LayerNorm(k+1),
+        // GEMM1(k+1) under the GI epilogue of k, and the rows of k+2 stream in under both.
+        int64_t item = blockIdx.x;
+        if (item < nitems) {
+            issue_item_loads<XT>(a, item, sStage, 0);
+            stage_and_normalize<XT>(a, item, sStage, sA1, sStat, true);
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            issue_gemm1();
+            if (item + G < nitems) issue_item_loads<XT>(a, item + G, sStage, 0);
         }
-        tc_fence_before_sync();
-        __syncthreads();
+        for (; item < nitems; item += G, phase ^= 1) {
+            mbar_wait(&bars[0], phase);
+            tc_fence_after_sync();
+            epilogue_u(tmem, lane_base, half, row, C, sA2);
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            issue_gemm2();
+            const int64_t nxt = item + G;
+            if (nxt < nitems) {
+                stage_and_normalize<XT>(a, nxt, sStage, sA1, sStat, true);       // A1 is free: GEMM1(item) has completed
+                fence_async_smem();
+                tc_fence_before_sync();
+                __syncthreads();
+                issue_gemm1();
+                if (nxt + G < nitems) issue_item_loads<XT>(a, nxt + G, sStage, 0);
+            }
+            mbar_wait(&bars[1], phase);
+            tc_fence_after_sync();
+            epilogue_gi(item);
+            tc_fence_before_sync();
+        }
+    } else {
+        for (int64_t item = blockIdx.x; item < nitems; item += G, phase ^= 1) {
+            stage_and_normalize<XT>(a, item, sStage, sA1, sStat, false);
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            issue_gemm1();
+            mbar_wait(&bars[0], phase);
+            tc_fence_after_sync();
+            epilogue_u(tmem, lane_base, half, row, C, sA2);
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            issue_gemm2();
+            mbar_wait(&bars[1], phase);
+            tc_fence_after_sync();
+            epilogue_gi(item);
+            tc_fence_before_sync();
+            __syncthreads();
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -403,7 +459,9 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
     if (prefetch && int64_t(blockIdx.x) < nitems) issue_item_loads<XT>(a, blockIdx.x, sStage, 0);
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
         if (pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }       // xhat / u / scratch tiles are free again
-        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, prefetch);
+        const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
+        if (prefetch) issue_tile_load(sScr, gin, NCH, row, half);                   // dGI tile: scratch is free, rows live elsewhere
+        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, prefetch, prefetch);
         fence_async_smem();
         tc_fence_before_sync();
         __syncthreads();
@@ -412,18 +470,15 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
             issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);   // pre
             mma_commit(&bars[0]);
         }
-        if (prefetch && item + gridDim.x < nitems) issue_item_loads<XT>(a, item + gridDim.x, sStage, 0);
-        // dGI tile of this item -> scratch (any raw rows there are dead), overlapping the MMA
-        {
-            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-            for (int ch = half; ch < NCH; ch += NSPLIT)
-                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, ch)) = *reinterpret_cast<const uint4*>(gin + tile_off(TM, row, ch));
-        }
+        if (!prefetch) issue_tile_load(sScr, gin, NCH, row, half);                  // the raw rows in scratch are dead now
+        const bool more = prefetch && item + gridDim.x < nitems;
+        if (more) issue_item_loads<XT>(a, item + gridDim.x, sStage, 0);
         mbar_wait(&bars[0], ph0);
         ph0 ^= 1;
         tc_fence_after_sync();
         if (MODE == 1) {
-            epilogue_u(tmem, lane_base, half, row, C, sB1, sA2);
+            epilogue_u(tmem, lane_base, half, row, C, sA2);
+            if (more) cp_async_wait<1>(); else cp_async_wait<0>();                  // the dGI tile has landed
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -444,9 +499,10 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int b = ch * 8 + e;
-                    if (v[e] + sB1[n0 + e] > 0.f) mask[b >> 5] |= 1u << (b & 31);
+                    if (v[e] > 0.f) mask[b >> 5] |= 1u << (b & 31);
                 }
             }
+            if (more) cp_async_wait<1>(); else cp_async_wait<0>();                  // the dGI tile has landed
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -500,6 +556,111 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
                 if (ok) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) atomicAdd(outbuf + size_t(orow) * CP + n0 + e, v[e]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---- K4b pipelined: dWih += dGI^T [u | 1] with the K1 software pipeline (dedicated row stage, two dGI buffers) -----------
+template <typename XT>
+__global__ void __launch_bounds__(NTH, 1) tc_front_bwd_wih_pipe_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
+    const int C = a.C, NC = a.NC, NCH = NC / 8;
+    const int MBW = NC > 128 ? 2 : 1;
+    unsigned char* sW1 = smem;
+    unsigned char* sA1 = sW1 + W1_BYTES;                  // xhat tile
+    unsigned char* sA2 = sA1 + A_BYTES;                   // u tile
+    unsigned char* sG = sA2 + A_BYTES;                    // two dGI tiles; the M-block over-read of the second runs into the stage
+    unsigned char* sStage = sG + 2u * NCH * TILE_CH;
+    float* sB1 = reinterpret_cast<float*>(sStage + STAGE_BYTES);
+    float* sStat = sB1 + CP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);   // 0: pre, 1: wgrad
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+    copy_image(sW1, a.ws.w1g, W1_BYTES);
+    for (int i = tid; i < CP; i += NTH) sB1[i] = a.ws.b1f[i];
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+    const uint32_t COL_ACC = 160;
+    const int64_t nitems = a.NT * a.T, G = gridDim.x;
+    auto gi_tile = [&](int64_t item) { return reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH; };
+    auto issue_gemm1 = [&]() {
+        if (tid == 0) {
+            tc_fence_after_sync();
+            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);
+            mma_commit(&bars[0]);
+        }
+    };
+    uint32_t ph0 = 0, ph1 = 0;
+    bool pending = false, started = false;
+    int64_t item = blockIdx.x;
+    if (item < nitems) {
+        issue_item_loads<XT>(a, item, sStage, 0);
+        issue_tile_load(sG, gi_tile(item), NCH, row, half);
+        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, true, true);
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        issue_gemm1();
+        if (item + G < nitems) issue_item_loads<XT>(a, item + G, sStage, 0);
+    }
+    for (int k = 0; item < nitems; item += G, ++k) {
+        const int64_t nxt = item + G;
+        unsigned char* gcur = sG + uint32_t(k & 1) * NCH * TILE_CH;
+        unsigned char* gnext = sG + uint32_t((k & 1) ^ 1) * NCH * TILE_CH;
+        mbar_wait(&bars[0], ph0);
+        ph0 ^= 1;
+        tc_fence_after_sync();
+        if (pending) { mbar_wait(&bars[1], ph1); ph1 ^= 1; pending = false; }     // u tile and the other dGI buffer are free
+        if (nxt < nitems) issue_tile_load(gnext, gi_tile(nxt), NCH, row, half);   // lands during this item's wgrad + LayerNorm(nxt)
+        epilogue_u(tmem, lane_base, half, row, C, sA2);
+        // dGI(item) landed: it is older than rows(nxt) [issued last iteration] only for k == 0; in steady state the
+        // groups in flight are rows(nxt), dGI(nxt) -> everything older (incl. dGI(item)) completed in LayerNorm's wait
+        if (k == 0) { if (nxt < nitems) cp_async_wait<2>(); else cp_async_wait<0>(); }
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            for (int mb = 0; mb < MBW; ++mb)
+                issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(gcur), 16 * mb, smem_u32(sA2), CP, started);
+            mma_commit(&bars[1]);
+        }
+        started = true;
+        pending = true;
+        if (nxt < nitems) {
+            stage_and_normalize<XT>(a, nxt, sStage, sA1, sStat, true, false);      // waits for rows(nxt) and dGI(nxt)
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            issue_gemm1();
+            if (nxt + G < nitems) issue_item_loads<XT>(a, nxt + G, sStage, 0);
+        }
+    }
+    if (pending) mbar_wait(&bars[1], ph1);
+    tc_fence_after_sync();
+    if (started) {
+        for (int mb = 0; mb < MBW; ++mb) {
+            const int orow = mb * 128 + row;
+            const bool ok = orow < NC;
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                const int n0 = HALF_COLS * half + ch * 8;
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + n0), v);
+                if (ok) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) atomicAdd(a.ws.dwih + size_t(orow) * CP + n0 + e, v[e]);
                 }
             }
         }
