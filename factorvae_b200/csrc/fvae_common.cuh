@@ -109,11 +109,16 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t step, int
     float u1 = u32_to_unit(r.x), u2 = u32_to_unit(r.y);
     return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
-// keep decision (prob 0.9) for (unit g, head k)
+// keep decision (prob 0.9) for (unit g, head k): a counter hash (two murmur-style finalizer rounds over
+// (seed, step, unit, head)) -- dropout masks do not need Philox strength and this is evaluated once per
+// (stock, head) in forward and again in backward.  Same shard-invariance contract as the eps stream.
 __device__ __forceinline__ bool philox_keep(uint64_t seed, uint64_t step, int64_t g, int k) {
-    uint4 r = philox4(seed, uint64_t(g), (step << 1) | 1ull | (uint64_t(k >> 2) << 32));
-    uint32_t v = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
-    return u32_to_unit(v) >= 0.1f;
+    uint32_t h = uint32_t(g) * 0x9E3779B1u ^ (uint32_t(uint64_t(g) >> 32) * 0x7FEB352Du) ^ (uint32_t(k) * 0x85EBCA77u)
+               ^ uint32_t(seed) ^ (uint32_t(seed >> 32) * 0xC2B2AE3Du) ^ (uint32_t(step) * 0x27D4EB2Fu);
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    h += uint32_t(k) * 0x9E3779B9u + uint32_t(g);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h >= 0x1999999Au;          // 2^32 / 10
 }
 #endif  // __CUDACC__
 

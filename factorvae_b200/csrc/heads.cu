@@ -163,7 +163,6 @@ __device__ __forceinline__ void stage_chunk(const HeadsArgs& a, const Smem& s, i
 // Sweeps use threads as (weight row, stock slice) pairs: with ncol rows and NT threads there are
 // NS = NT / ncol slices, slice s takes stocks s, s+NS, ... of each chunk, and the partial online-softmax
 // states of a row are merged once per date.  Nobody idles at the chunk barriers.
-constexpr int MAXNS = 4;       // cap on slices of the statistics sweep (bounds the merge scratch)
 
 __device__ __forceinline__ void merge_state(float& m, float& l, float m2, float l2, float& sc1, float& sc2) {
     const float mm = fmaxf(m, m2);
@@ -187,16 +186,26 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     // ---- pass A: online column softmax over the stocks for encoder (M) and attention (K) columns
     const int colA0 = a.predict ? M : 0;
     const int ncolA = a.predict ? K : M + K;
-    const int cpb = ncolA < NT ? ncolA : NT;                     // columns per batch
-    const int NS = (NT / cpb) < MAXNS ? (NT / cpb) : MAXNS;      // stock slices
-    float* scrE = s.F;                                            // [cpb][NS][3]      (m, l, accy)      -- only M of them used
-    float* scrA = s.F + size_t(MAXNS) * 3 * M;                    // [K][NS][HP + 2]   (m, l, accp[HP])
+    // Thread -> (column, stock slice).  Encoder columns are cheap (dot + exp) and get one thread each; attention
+    // columns (mask hash, ReLU, exp, pooled e-accumulation) cost ~3x as much per stock and get the remaining
+    // threads as NS slices each, so nobody idles at the chunk barriers.
+    const int nenc = a.predict ? 0 : M;
+    const bool one_batch = ncolA <= NT;
+    const int cpb = one_batch ? ncolA : NT;                       // columns per batch
+    int NS = 1;
+    if (one_batch) { NS = (NT - nenc) / K; NS = NS < 1 ? 1 : (NS > 8 ? 8 : NS); }
+    float* scrA = s.F;                                            // [K][NS][HP + 2]   (m, l, accp[HP])
     for (int cb = 0; cb < ncolA; cb += cpb) {
-        const int cl = tid % cpb, slice = tid / cpb;
+        int cl, slice;
+        if (one_batch) {
+            if (tid < nenc) { cl = tid; slice = 0; }
+            else { cl = nenc + (tid - nenc) % K; slice = (tid - nenc) / K; }
+        } else { cl = tid; slice = 0; }
         const int c = colA0 + cb + cl;
-        const bool act = slice < NS && (cb + cl) < ncolA;
         const bool is_att = c >= M;
+        const bool act = (cb + cl) < ncolA && slice < (is_att ? NS : 1);
         const int k = c - M;
+        const int nsl = is_att ? NS : 1;
         float w[HP];
         load_row<HP>(w, is_att ? a.sv.G + size_t(act ? k : 0) * H : a.w.Wp + size_t(act ? c : 0) * H, H, act);
         const float bias = !act ? 0.f : (is_att ? a.sv.cvec[k] : a.w.bp[c]);
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
             if (tid < CH) s.ys[tid] = (!a.predict && tid < cn) ? a.y[p0 + i0 + tid] : 0.f;
             __syncthreads();
             if (!act) continue;
-            for (int i = slice; i < cn; i += NS) {
+            for (int i = slice; i < cn; i += nsl) {
                 const float* er = s.Es + i * HP;
                 float x = dot_row<HP>(w, er) + bias;
                 if (is_att) {
@@ -242,38 +251,27 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
                 }
             }
         }
-        // ---- merge the NS partial states of each column
+        // ---- merge the NS partial states of each attention column
         __syncthreads();
-        if (act && slice > 0) {
-            if (is_att) {
-                float* o = scrA + (size_t(k) * NS + slice) * (HP + 2);
-                o[0] = m; o[1] = l; s.bad[k] = 0;
+        if (act && is_att && slice > 0) {
+            float* o = scrA + (size_t(k) * NS + slice) * (HP + 2);
+            o[0] = m; o[1] = l;
 #pragma unroll
-                for (int h = 0; h < HP; ++h) o[2 + h] = accp[h];
-            } else {
-                float* o = scrE + (size_t(c) * NS + slice) * 3;
-                o[0] = m; o[1] = l; o[2] = accy;
-            }
+            for (int h = 0; h < HP; ++h) o[2 + h] = accp[h];
         }
         if (act && slice == 0 && is_att) s.bad[k] = 0;
         __syncthreads();
         if (act && bad) atomicOr(&s.bad[k], 1);
         __syncthreads();
         if (act && slice == 0) {
-            for (int q = 1; q < NS; ++q) {
-                float sc1, sc2;
-                if (is_att) {
+            if (is_att) {
+                for (int q = 1; q < NS; ++q) {
+                    float sc1, sc2;
                     const float* o = scrA + (size_t(k) * NS + q) * (HP + 2);
                     if (o[1] > 0.f || o[1] != o[1]) {          // that slice saw at least one stock
                         merge_state(m, l, o[0], o[1], sc1, sc2);
 #pragma unroll
                         for (int h = 0; h < HP; ++h) accp[h] = accp[h] * sc1 + o[2 + h] * sc2;
-                    }
-                } else {
-                    const float* o = scrE + (size_t(c) * NS + q) * 3;
-                    if (o[1] > 0.f || o[1] != o[1]) {
-                        merge_state(m, l, o[0], o[1], sc1, sc2);
-                        accy = accy * sc1 + o[2] * sc2;
                     }
                 }
             }
@@ -651,10 +649,19 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
 
     // ---- pass C2: Z sweep -> weight gradients (registers) and dE
     // thread = (weight row c, stock slice): rows per batch cpb2, NS2 slices, NB batches of rows
-    const int cpb2 = NF < NT ? NF : NT;
-    const int NS2 = NT / cpb2;
-    const int mycl = tid % cpb2, myslice = tid / cpb2;
-    const bool slice_ok = myslice < NS2;
+    // NB == 1 (all rows fit one batch): encoder / beta / alpha rows get one thread, attention rows (two sweeps,
+    // mask hash, exp) get NS2 slices each.  NB > 1: plain row = b*NT + tid.
+    int NS2 = 1;
+    if (NB == 1) { NS2 = (NT - M - K - H) / K; NS2 = NS2 < 1 ? 1 : (NS2 > 8 ? 8 : NS2); }
+    int mycl = tid, myslice = 0;
+    bool slice_ok = true;
+    if (NB == 1) {
+        if (tid < M) { mycl = tid; }
+        else if (tid < M + K * NS2) { mycl = M + (tid - M) % K; myslice = (tid - M) / K; }
+        else { mycl = M + K + (tid - M - K * NS2); slice_ok = mycl < NF; }
+    }
+    const int cpb2 = NT;
+    const int mynsl = (NB == 1 && mycl >= M && mycl < M + K) ? NS2 : 1;
     const int cpbA = H < NT ? H : NT;                     // alpha rows in S1c
     const int NSA = NT / cpbA;
     constexpr int PPS = NT / CH;
@@ -691,19 +698,19 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                 const ColRef cr = col_ref(a, c);
                 float w[HP];
                 if (cr.kind == 1 && bad[cr.idx]) {
-                    for (int i = myslice; i < cn; i += NS2) { Z[i * ZLD + c] = 0.f; Aatt[i * ALD + cr.idx] = 0.f; }
+                    for (int i = myslice; i < cn; i += mynsl) { Z[i * ZLD + c] = 0.f; Aatt[i * ALD + cr.idx] = 0.f; }
                 } else {
                     load_row<HP>(w, cr.w, H, true);
                     if (cr.kind == 0) {                         // encoder: dlogit = w_ij dyp_j (y_i - yp_j)
                         const float mj = encm[c], lj = encl[c], dj = dyp[c], ypj = yp[c];
-                        for (int i = myslice; i < cn; i += NS2) {
+                        for (int i = myslice; i < cn; i += mynsl) {
                             const float x = dot_row<HP>(w, Es + i * HP) + cr.bias;
                             Z[i * ZLD + c] = expf(x - mj) / lj * dj * (ys[i] - ypj);
                         }
                     } else if (cr.kind == 1) {                  // attention: a_ik now, ds_ik after the dp sweep
                         const int k = cr.idx;
                         const float mk = attm[k], lk = attl[k];
-                        for (int i = myslice; i < cn; i += NS2) {
+                        for (int i = myslice; i < cn; i += mynsl) {
                             float x = (dot_row<HP>(w, Es + i * HP) + cr.bias) / tau;
                             const float kf = keep_factor(a, p0 + i0 + i, k);
                             x = x * kf;
@@ -714,18 +721,18 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                         }
                         load_row<HP>(w, dps + k * H, H, true);   // second sweep with dp_k
                         const float pk = pdp[k];
-                        for (int i = myslice; i < cn; i += NS2) {
+                        for (int i = myslice; i < cn; i += mynsl) {
                             const float dr = Aatt[i * ALD + k] * (dot_row<HP>(w, Es + i * HP) - pk);
                             Z[i * ZLD + c] *= dr;
                         }
                     } else if (cr.kind == 2) {                  // beta: mu_z dmu_y + 2 beta sigma_z^2 dv
                         const float mz = muz[cr.idx], sz2 = sgz[cr.idx] * sgz[cr.idx];
-                        for (int i = myslice; i < cn; i += NS2) {
+                        for (int i = myslice; i < cn; i += mynsl) {
                             const float bt = dot_row<HP>(w, Es + i * HP) + cr.bias;
                             Z[i * ZLD + c] = mz * dmy[i] + 2.f * bt * sz2 * dvv[i];
                         }
                     } else {                                    // alpha hidden: keep pre-activation for S1b/S1c
-                        for (int i = myslice; i < cn; i += NS2) Z[i * ZLD + c] = dot_row<HP>(w, Es + i * HP) + cr.bias;
+                        for (int i = myslice; i < cn; i += mynsl) Z[i * ZLD + c] = dot_row<HP>(w, Es + i * HP) + cr.bias;
                     }
                 }
             }
@@ -775,7 +782,7 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         for (int b = 0; b < NB; ++b) {
             const int c = b * cpb2 + mycl;
             if (c < NF && slice_ok) {
-                for (int i = myslice; i < cn; i += NS2) {
+                for (int i = myslice; i < cn; i += mynsl) {
                     const float z = Z[i * ZLD + c];
                     accb[b] += z;
                     const float4* e4 = reinterpret_cast<const float4*>(Es + i * HP);
@@ -863,7 +870,7 @@ size_t fwd_smem_bytes(int HP, int H, int K, int M) {
     size_t f = size_t(CH) * HP + 3 * CH + 32 + M + 5 * size_t(K) + 2 * size_t(K) * H;
     size_t fl = size_t(CH) * ((K + H) | 1);
     size_t hm = size_t(K) * H;
-    size_t mg = size_t(MAXNS) * (3 * size_t(M) + size_t(K) * (HP + 2));     // merge scratch of the statistics sweep
+    size_t mg = size_t(NT) * (HP + 2);                                       // merge scratch of the statistics sweep
     size_t mx = fl > hm ? fl : hm;
     if (mg > mx) mx = mg;
     return (f + mx) * sizeof(float);
