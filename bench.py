@@ -19,7 +19,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -52,39 +51,44 @@ def build_params(H, K, M, seed=42):
     return {k: v.detach().clone() for k, v in model.state_dict().items()}
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING warm-up + the timed region (one `nvidia-smi -lms 100`
+    child process; stopped by its exact PID)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu_index, self.rows, self._halt = gpu_index, [], threading.Event()
+        self.gpu_index, self.proc = gpu_index, None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                r = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[c.strip() for c in ln.split(",")] for ln in out.strip().splitlines() if ln.count(",") >= 8]
+        busy = [r for r in rows if r[3].replace(".", "").isdigit() and float(r[3]) > 250.0] or rows      # samples under load
+        sm = sorted(float(r[1]) for r in busy if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for nm, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len(busy)}
 
 
 def run_reference(args, wl, rank, world):
@@ -187,12 +191,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    t_warm = time.perf_counter()
+    for _ in range(args.warmup):
+        one_step()
+    while time.perf_counter() - t_warm < 0.5:       # keep the GPU under load long enough for a few clock samples
+        one_step()
+    barrier()
     l0 = lib.fvae_debug_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -57,6 +57,8 @@ struct TcWs {
     float *b1f, *bgi, *bhn;                         // [CP], [NC], [HP]
     __nv_bfloat16 *gi;      // [NT][T][NC/8][128][8]   gate pre-activations, then (backward) their gradients
     __nv_bfloat16 *hall;    // [NT][T][HP/8][128][8]   h_t operand tiles (column H = 1)
+    __nv_bfloat16 *u;       // [NT][T][CP/8][128][8]   u = LeakyReLU(pre) operand tiles (column C = 1), saved for backward
+    unsigned long long *mask;  // [NT][T][4][128]      LeakyReLU' sign bits of my 40 columns (bit b: pre > 0)
     float *q;               // [2*128][CP]  Q = dpre^T [xhat|1]
     float *dwih;            // [2*128][CP]  dGI^T [u|1]   (permuted rows)
     int64_t bytes;
@@ -78,6 +80,8 @@ TcWs carve_tc(const FeDims& d, void* base) {
     w.bhn = reinterpret_cast<float*>(take(HP * 4));
     w.gi = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(NC / 8) * TILE_CH));
     w.hall = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(HP / 8) * TILE_CH));
+    w.u = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(A_BYTES)));
+    w.mask = reinterpret_cast<unsigned long long*>(take(NT * d.T * int64_t(4 * TM * 8)));
     w.q = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
     w.dwih = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
     w.bytes = p - static_cast<char*>(base);
@@ -581,22 +585,33 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     const bool bf = x.dtype == FVAE_BF16;
     const bool pf0 = bf && base0 + STAGE_BYTES <= kMaxSmem, pf1 = bf && base1 + STAGE_BYTES <= kMaxSmem;
     const size_t smem0 = base0 + (pf0 ? STAGE_BYTES : 0), smem1 = base1 + (pf1 ? STAGE_BYTES : 0);
-    if (bf) {
+    const size_t smemq = size_t(NC / 8) * CP * 16 + 3 * A_BYTES + STAGE_BYTES + tail - CP * 4;
+    if (bf && smemq <= kMaxSmem) {
+        a.prefetch = 1;
+        if ((rc = launch_smem(tc_q_kernel<__nv_bfloat16>, grid, smemq, st, a)) != 0) return rc;
+    } else if (bf) {
         a.prefetch = pf0;
         if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 0>, grid, smem0, st, a)) != 0) return rc;
-        const size_t pipe = W1_BYTES + 2 * A_BYTES + 2 * size_t(NC / 8) * TILE_CH + STAGE_BYTES + tail;
-        if (pipe <= kMaxSmem) {
-            a.prefetch = 1;
-            if ((rc = launch_smem(tc_front_bwd_wih_pipe_kernel<__nv_bfloat16>, grid, pipe, st, a)) != 0) return rc;
-        } else {
-            a.prefetch = pf1;
-            if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 1>, grid, smem1, st, a)) != 0) return rc;
-        }
     } else {
         a.prefetch = 0;
         if ((rc = launch_smem(tc_front_bwd_kernel<float, 0>, grid, smem0, st, a)) != 0) return rc;
-        if ((rc = launch_smem(tc_front_bwd_kernel<float, 1>, grid, smem1, st, a)) != 0) return rc;
     }
+    {   // dWih from the u tiles saved by the forward kernel (the panel is not touched)
+        const size_t per_stage = size_t(NC / 8) * TILE_CH + A_BYTES;
+        cudaError_t ce2;
+        if (3 * per_stage + 64 <= kMaxSmem) {
+            const size_t smemw = 3 * per_stage + 64;
+            if ((ce2 = cudaFuncSetAttribute(tc_wih_from_u_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemw))) != cudaSuccess) return int(ce2);
+            tc_wih_from_u_kernel<3><<<grid, WIH_THREADS, smemw, st>>>(a); count_launch();
+        } else {
+            const size_t smemw = 2 * per_stage + 64;
+            if (smemw > kMaxSmem) return FVAE_ERR_LIMIT;
+            if ((ce2 = cudaFuncSetAttribute(tc_wih_from_u_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemw))) != cudaSuccess) return int(ce2);
+            tc_wih_from_u_kernel<2><<<grid, WIH_THREADS, smemw, st>>>(a); count_launch();
+        }
+        if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
+    }
+    (void)smem1; (void)pf1;
     PostArgs p{d.C, d.H, NC, w.ln_w, w.ln_b, w.W1, ws.q, ws.dwih, gr};
     tc_post_kernel<<<64, 256, 0, st>>>(p); count_launch();
     return int(cudaGetLastError());

@@ -274,13 +274,19 @@ __device__ __forceinline__ uint32_t lrelu_pack(float lo, float hi) {
     const __nv_bfloat162 y = __hmax2(x, __hmul2(x, __floats2bfloat162_rn(kLeakySlope, kLeakySlope)));
     return *reinterpret_cast<const uint32_t*>(&y);
 }
-__device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, int half, int row, int C, unsigned char* tile) {
+__device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, int half, int row, int C, unsigned char* tile,
+                                           unsigned char* gtile = nullptr, unsigned long long* gmask = nullptr) {
     const int c0 = HALF_COLS * half;
     const int one_ch = (C >= c0 && C < c0 + HALF_COLS) ? (C - c0) >> 3 : -1;       // warp-uniform
+    unsigned long long bits = 0ull;
 #pragma unroll
     for (int ch = 0; ch < HALF_CH; ++ch) {
         float v[8];
         tmem_ld8(tmem_addr(tmem, lane_base, c0 + ch * 8), v);
+        if (gmask) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bits |= (unsigned long long)(v[e] > 0.f) << (ch * 8 + e);
+        }
         uint32_t w0 = lrelu_pack(v[0], v[1]), w1 = lrelu_pack(v[2], v[3]), w2 = lrelu_pack(v[4], v[5]), w3 = lrelu_pack(v[6], v[7]);
         if (ch == one_ch) {
             const int e = (C - c0) & 7, q = e >> 1;
@@ -290,8 +296,11 @@ __device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, in
             else if (q == 2) w2 = (w2 & keep) | one;
             else w3 = (w3 & keep) | one;
         }
-        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) = make_uint4(w0, w1, w2, w3);
+        const uint4 pk = make_uint4(w0, w1, w2, w3);
+        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) = pk;
+        if (gtile) *reinterpret_cast<uint4*>(gtile + tile_off(TM, row, HALF_CH * half + ch)) = pk;     // saved for backward
     }
+    if (gmask) gmask[half * TM + row] = bits;
 }
 
 // ---- K1: front forward ---------------------------------------------------------------------------------------
@@ -369,7 +378,8 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
         for (; item < nitems; item += G, phase ^= 1) {
             mbar_wait(&bars[0], phase);
             tc_fence_after_sync();
-            epilogue_u(tmem, lane_base, half, row, C, sA2);
+            epilogue_u(tmem, lane_base, half, row, C, sA2, reinterpret_cast<unsigned char*>(a.ws.u) + size_t(item) * A_BYTES,
+                       a.ws.mask + size_t(item) * 4 * TM);
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -397,7 +407,8 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
             issue_gemm1();
             mbar_wait(&bars[0], phase);
             tc_fence_after_sync();
-            epilogue_u(tmem, lane_base, half, row, C, sA2);
+            epilogue_u(tmem, lane_base, half, row, C, sA2, reinterpret_cast<unsigned char*>(a.ws.u) + size_t(item) * A_BYTES,
+                       a.ws.mask + size_t(item) * 4 * TM);
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -661,6 +672,260 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_bwd_wih_pipe_kernel(ItemArgs 
                 if (ok) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) atomicAdd(a.ws.dwih + size_t(orow) * CP + n0 + e, v[e]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---- K4b: dWih += dGI^T [u | 1] from the u tiles saved by K1 -- pure streaming: two operand tiles per item arrive by
+// cp.async into a 3-deep ring while the weight-gradient MMAs of older items run; bounded by HBM (61 KB per item).
+constexpr int WIH_THREADS = 256;
+template <int WIH_STAGES>
+__global__ void __launch_bounds__(WIH_THREADS, 1) tc_wih_from_u_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int NC = a.NC, NCH = NC / 8;
+    const int MBW = NC > 128 ? 2 : 1;
+    const uint32_t g_bytes = uint32_t(NCH) * TILE_CH, stage_bytes = g_bytes + A_BYTES;      // [dGI tile | u tile]
+    unsigned char* sRing = smem;                                   // WIH_STAGES x [dGI | u]; the dGI M-block over-read runs into u
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + WIH_STAGES * stage_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WIH_STAGES);
+    if (tid == 0) { for (int i = 0; i < WIH_STAGES; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const int64_t nitems = a.NT * a.T, G = gridDim.x;
+    auto issue_loads = [&](int64_t item, int stg) {
+        unsigned char* dst = sRing + uint32_t(stg) * stage_bytes;
+        const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * g_bytes;
+        const unsigned char* usrc = reinterpret_cast<const unsigned char*>(a.ws.u) + size_t(item) * A_BYTES;
+        for (uint32_t i = tid; i < g_bytes / 16; i += WIH_THREADS) cp_async16(smem_u32(dst + i * 16), gsrc + i * 16);
+        for (uint32_t i = tid; i < A_BYTES / 16; i += WIH_THREADS) cp_async16(smem_u32(dst + g_bytes + i * 16), usrc + i * 16);
+        cp_async_commit();
+    };
+    // ring: loads run WIH_STAGES-1 items ahead of the MMAs
+    int64_t next_load = blockIdx.x;
+    for (int sidx = 0; sidx < WIH_STAGES - 1; ++sidx) {
+        if (next_load < nitems) issue_loads(next_load, sidx); else cp_async_commit();
+        next_load += G;
+    }
+    uint32_t phase_bits = 0;           // per-stage mbarrier phases
+    bool started = false;
+    int k = 0;
+    for (int64_t item = blockIdx.x; item < nitems; item += G, ++k) {
+        const int stg = k % WIH_STAGES;
+        // stage (k + STAGES - 1) % STAGES was used by item k-1: its MMAs must be done before it is refilled
+        const int refill = (k + WIH_STAGES - 1) % WIH_STAGES;
+        if (k > 0) { mbar_wait(&bars[refill], (phase_bits >> refill) & 1u); phase_bits ^= 1u << refill; }
+        if (next_load < nitems) issue_loads(next_load, refill); else cp_async_commit();
+        next_load += G;
+        cp_async_wait<WIH_STAGES - 1>();          // the loads of item k have landed
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            const uint32_t base = smem_u32(sRing + uint32_t(stg) * stage_bytes);
+            for (int mb = 0; mb < MBW; ++mb) issue_wgrad(tmem, uint32_t(mb) * CP, base, 16 * mb, base + g_bytes, CP, started);
+            mma_commit(&bars[stg]);
+        }
+        started = true;
+    }
+    // drain: the last item's MMAs (commits are ordered, so its barrier covers everything before)
+    if (k > 0) { const int last = (k - 1) % WIH_STAGES; mbar_wait(&bars[last], (phase_bits >> last) & 1u); }
+    cp_async_wait<0>();
+    tc_fence_after_sync();
+    if (started) {
+        const int row = tid & (TM - 1), half = tid >> 7;          // 2 column halves of 80
+        const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+        for (int mb = 0; mb < MBW; ++mb) {
+            const int orow = mb * 128 + row;
+            const bool ok = orow < NC;
+            for (int ch = 0; ch < KCH / 2; ++ch) {
+                const int n0 = (CP / 2) * half + ch * 8;
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, uint32_t(mb) * CP + n0), v);
+                if (ok) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) atomicAdd(a.ws.dwih + size_t(orow) * CP + n0 + e, v[e]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---- K4a: Q += dpre^T [xhat | 1] without recomputing GEMM 1 ------------------------------------------------------------
+// The LeakyReLU' sign bits were saved by K1, so backward needs xhat (LayerNorm of the raw rows), du = dGI . W_ih and the
+// weight-gradient MMAs only.  Software pipeline per item k:
+//     MMA du(k)  ||  LayerNorm(k+1) in registers      ->  dpre epilogue  ->  MMA Q(k)  ->  xhat(k+1) stored, loads of k+2
+// Q is kept in three TMEM blocks so that no operand tile is over-read:  A: rows o<128 (A = dpre, B = xhat, N = 160);
+// B0/B1: rows o in [128,160) computed transposed (A = xhat M-blocks, B = dpre chunks 16..19, N = 32).
+template <typename XT>
+__device__ __forceinline__ void layernorm_regs(const ItemArgs& a, int64_t st, int t, const unsigned char* stage, float* sStat,
+                                               float (&v)[HALF_COLS]) {
+    static_assert(sizeof(XT) == 2, "single-pass staging only");
+    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7, C = a.C;
+    const int c0 = HALF_COLS * half;
+    const bool partial = c0 + HALF_COLS > C;
+    const int64_t s = st * TM + row;
+    const uint32_t off = s < a.S ? uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u) : 0u;
+    fetch_half(static_cast<const XT*>(nullptr), stage + size_t(row) * slot_bytes<XT>(C), off, half, v);
+    if (partial) {
+#pragma unroll
+        for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = 0.f;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < HALF_COLS; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+    sStat[half * TM + row] = s1;
+    sStat[NSPLIT * TM + half * TM + row] = s2;
+    __syncthreads();
+    const float inv_c = 1.f / float(C);
+    const float mean = (sStat[row] + sStat[TM + row] + sStat[2 * TM + row] + sStat[3 * TM + row]) * inv_c;
+    const float ex2 = (sStat[4 * TM + row] + sStat[5 * TM + row] + sStat[6 * TM + row] + sStat[7 * TM + row]) * inv_c;
+    const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + kLnEps);
+    const float shift = -mean * rstd;
+#pragma unroll
+    for (int j = 0; j < HALF_COLS; ++j) v[j] = fmaf(v[j], rstd, shift);
+    if (partial) {
+#pragma unroll
+        for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = (c0 + j == C) ? 1.f : 0.f;
+    }
+}
+__device__ __forceinline__ void store_xhat(const float (&v)[HALF_COLS], unsigned char* tile, int row, int half) {
+#pragma unroll
+    for (int ch = 0; ch < HALF_CH; ++ch)
+        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
+            make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
+                       pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(NTH, 1) tc_q_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
+    const int NC = a.NC, NCH = NC / 8;
+    unsigned char* sWihT = smem;                                   // [NCH][CP][16]   B of du = dGI . W_ih
+    unsigned char* sA1 = sWihT + uint32_t(NCH) * CP * 16;          // xhat tile; its M-block over-read runs into sS
+    unsigned char* sS = sA1 + A_BYTES;                             // 2 x [dGI tile -> dpre tile]
+    unsigned char* sStage = sS + 2 * A_BYTES;
+    float* sStat = reinterpret_cast<float*>(sStage + STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);      // 0: du, 1: Q
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
+    for (uint32_t i = tid; i < 2 * A_BYTES / 16; i += NTH) reinterpret_cast<uint4*>(sS)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+    constexpr uint32_t COL_DU = 0, COL_QA = 160, COL_QB0 = 320, COL_QB1 = 352;
+    const int64_t nitems = a.NT * a.T, G = gridDim.x;
+    auto gi_tile = [&](int64_t it) { return reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(it) * NCH * TILE_CH; };
+    auto commit_rows = [&](int64_t it) { if (it < nitems) issue_item_loads<XT>(a, it, sStage, 0); else cp_async_commit(); };
+    auto commit_dgi = [&](int64_t it, int b) { if (it < nitems) issue_tile_load(sS + uint32_t(b) * A_BYTES, gi_tile(it), NCH, row, half); else cp_async_commit(); };
+    uint32_t ph0 = 0, ph1 = 0;
+    bool started = false;
+    int64_t item = blockIdx.x;
+    float v[HALF_COLS];
+    if (item < nitems) {
+        commit_rows(item);
+        commit_dgi(item, 0);
+        cp_async_wait<1>();                       // rows(item)
+        __syncthreads();
+        layernorm_regs<XT>(a, item / a.T, int(item % a.T), sStage, sStat, v);
+        store_xhat(v, sA1, row, half);
+        __syncthreads();                          // every thread is done with the stage
+        commit_rows(item + G);
+        commit_dgi(item + G, 1);
+    }
+    for (int k = 0; item < nitems; item += G, ++k) {
+        const int b = k & 1;
+        const int64_t nxt = item + G;
+        unsigned char* sD = sS + uint32_t(b) * A_BYTES;
+        const unsigned long long mbits = a.ws.mask[size_t(item) * 4 * TM + half * TM + row];
+        cp_async_wait<2>();                       // dGI(item) has landed (rows(nxt), dGI(nxt) may still fly)
+        fence_async_smem();                       // also publishes xhat(item)
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            issue_row_gemm(tmem, COL_DU, smem_u32(sD), smem_u32(sWihT), CP, CP, NC / 16);       // du = dGI . W_ih
+            mma_commit(&bars[0]);
+        }
+        if (nxt < nitems) {                       // LayerNorm(nxt) in registers while the MMA runs
+            cp_async_wait<1>();                   // rows(nxt)
+            __syncthreads();
+            layernorm_regs<XT>(a, nxt / a.T, int(nxt % a.T), sStage, sStat, v);
+        }
+        mbar_wait(&bars[0], ph0);
+        ph0 ^= 1;
+        tc_fence_after_sync();
+        // dpre = du * LeakyReLU'(pre) -> bf16 tile over the dead dGI tile
+#pragma unroll
+        for (int ch = 0; ch < HALF_CH; ++ch) {
+            float d[8];
+            tmem_ld8(tmem_addr(tmem, lane_base, COL_DU + HALF_COLS * half + ch * 8), d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[e] *= ((mbits >> (ch * 8 + e)) & 1ull) ? 1.f : kLeakySlope;
+            *reinterpret_cast<uint4*>(sD + tile_off(TM, row, HALF_CH * half + ch)) =
+                make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+        }
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            issue_wgrad(tmem, COL_QA, smem_u32(sD), 0, smem_u32(sA1), CP, started);                       // rows o < 128
+            issue_wgrad(tmem, COL_QB0, smem_u32(sA1), 0, smem_u32(sD) + 16 * TILE_CH, 32, started);      // rows o >= 128, i < 128
+            issue_wgrad(tmem, COL_QB1, smem_u32(sA1), 16, smem_u32(sD) + 16 * TILE_CH, 32, started);     // rows o >= 128, i >= 128
+            mma_commit(&bars[1]);
+        }
+        started = true;
+        mbar_wait(&bars[1], ph1);                 // xhat tile and this dGI/dpre buffer are free again
+        ph1 ^= 1;
+        tc_fence_after_sync();
+        if (nxt < nitems) store_xhat(v, sA1, row, half);
+        __syncthreads();                          // LayerNorm(nxt) no longer needs the stage (all threads passed it)
+        commit_rows(nxt + G);
+        commit_dgi(nxt + G, b);
+    }
+    cp_async_wait<0>();
+    tc_fence_after_sync();
+    if (started) {
+        const int C = a.C;
+        // block A: lane = o (< 128), my 40 columns i
+        for (int ch = 0; ch < HALF_CH; ++ch) {
+            const int n0 = HALF_COLS * half + ch * 8;
+            float d[8];
+            tmem_ld8(tmem_addr(tmem, lane_base, COL_QA + n0), d);
+            if (row < C) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(a.ws.q + size_t(row) * CP + n0 + e, d[e]);
+            }
+        }
+        // blocks B0 / B1: lane = i (B0: i = row, B1: i = 128 + row), my 8 columns o' = 8*half .. -> o = 128 + o'
+        for (int blk = 0; blk < 2; ++blk) {
+            float d[8];
+            tmem_ld8(tmem_addr(tmem, lane_base, (blk == 0 ? COL_QB0 : COL_QB1) + 8 * half), d);
+            const int i = blk * 128 + row;
+            if (i < CP) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int o = 128 + 8 * half + e;
+                    if (o < C) atomicAdd(a.ws.q + size_t(o) * CP + i, d[e]);
                 }
             }
         }
