@@ -14,9 +14,12 @@
 //   K3 gru_bwd    per tile : BPTT; per step MMA gh (recompute), gate gradients (fp32) -> dGI tile (in place)
 //                            and dgh tile, MMA dh += dgh . W_hh, MMA dW_hh += dgh^T . [h_{t-1} | 1] (TMEM
 //                            accumulators live across all tiles of the CTA; one flush per CTA)
-//   K4a front_bwd_w1 / K4b front_bwd_wih per item: recompute xhat, pre (MMA); du = dGI . W_ih (MMA);
-//                            dpre = du * LeakyReLU'; Q += dpre^T . [xhat | 1]; dWih += dGI^T . [u | 1]
-//                            (weight-gradient MMAs read the SAME smem tiles as MN-major operands)
+//   K1 also saves, per item, the xhat and u operand tiles (bf16) and the LeakyReLU' sign bits, so backward never
+//   touches the panel again and never recomputes GEMM 1:
+//   K4a q_from_tiles per item: du = dGI . W_ih (MMA), dpre = du * LeakyReLU' (epilogue), Q += dpre^T . [xhat | 1]
+//   K4b wih_from_u   per item: dWih += dGI^T . [u | 1]
+//                            (both stream their operand tiles through a cp.async ring; the weight-gradient MMAs read
+//                             the SAME smem tiles as MN-major operands; accumulators live in TMEM for the whole kernel)
 //   K5 post                : dW1 = Q diag(gamma) + db1 beta^T, dgamma = sum_o W1 .* Q, dbeta = W1^T db1,
 //                            un-permute dW_ih / db_ih.   (x is data: no LayerNorm input gradient, so the
 //                            dxn = dpre . W1 contraction of the reference's autograd is never computed)
@@ -57,6 +60,7 @@ struct TcWs {
     float *b1f, *bgi, *bhn;                         // [CP], [NC], [HP]
     __nv_bfloat16 *gi;      // [NT][T][NC/8][128][8]   gate pre-activations, then (backward) their gradients
     __nv_bfloat16 *hall;    // [NT][T][HP/8][128][8]   h_t operand tiles (column H = 1)
+    __nv_bfloat16 *xh;      // [NT][T][CP/8][128][8]   xhat = LayerNorm(x) operand tiles (column C = 1), saved for backward
     __nv_bfloat16 *u;       // [NT][T][CP/8][128][8]   u = LeakyReLU(pre) operand tiles (column C = 1), saved for backward
     unsigned long long *mask;  // [NT][T][4][128]      LeakyReLU' sign bits of my 40 columns (bit b: pre > 0)
     float *q;               // [2*128][CP]  Q = dpre^T [xhat|1]
@@ -80,6 +84,7 @@ TcWs carve_tc(const FeDims& d, void* base) {
     w.bhn = reinterpret_cast<float*>(take(HP * 4));
     w.gi = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(NC / 8) * TILE_CH));
     w.hall = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(HP / 8) * TILE_CH));
+    w.xh = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(A_BYTES)));
     w.u = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(A_BYTES)));
     w.mask = reinterpret_cast<unsigned long long*>(take(NT * d.T * int64_t(4 * TM * 8)));
     w.q = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
@@ -579,22 +584,21 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     if (ce != cudaSuccess) return int(ce);
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
-    const size_t tail = (CP + 2 * NSPLIT * TM) * 4 + 64;
-    const size_t base0 = W1_BYTES + size_t(NC / 8) * CP * 16 + A_BYTES + 32 * TILE_CH + tail;
-    const size_t base1 = W1_BYTES + 2 * A_BYTES + size_t(NC > 128 ? 32 : 21) * TILE_CH + tail;
-    const bool bf = x.dtype == FVAE_BF16;
-    const bool pf0 = bf && base0 + STAGE_BYTES <= kMaxSmem, pf1 = bf && base1 + STAGE_BYTES <= kMaxSmem;
-    const size_t smem0 = base0 + (pf0 ? STAGE_BYTES : 0), smem1 = base1 + (pf1 ? STAGE_BYTES : 0);
-    const size_t smemq = size_t(NC / 8) * CP * 16 + 3 * A_BYTES + STAGE_BYTES + tail - CP * 4;
-    if (bf && smemq <= kMaxSmem) {
-        a.prefetch = 1;
-        if ((rc = launch_smem(tc_q_kernel<__nv_bfloat16>, grid, smemq, st, a)) != 0) return rc;
-    } else if (bf) {
-        a.prefetch = pf0;
-        if ((rc = launch_smem(tc_front_bwd_kernel<__nv_bfloat16, 0>, grid, smem0, st, a)) != 0) return rc;
-    } else {
-        a.prefetch = 0;
-        if ((rc = launch_smem(tc_front_bwd_kernel<float, 0>, grid, smem0, st, a)) != 0) return rc;
+    {   // Q from the saved xhat tiles / mask bits (the panel is not touched)
+        const size_t per_stage = A_BYTES + A_BYTES;          // xhat tile + [dGI -> dpre] tile
+        const size_t wt = size_t(NC / 8) * CP * 16;
+        cudaError_t ce2;
+        if (wt + 3 * per_stage + 64 <= kMaxSmem) {
+            const size_t smemq = wt + 3 * per_stage + 64;
+            if ((ce2 = cudaFuncSetAttribute(tc_q_from_tiles_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemq))) != cudaSuccess) return int(ce2);
+            tc_q_from_tiles_kernel<3><<<grid, NTH, smemq, st>>>(a); count_launch();
+        } else {
+            const size_t smemq = wt + 2 * per_stage + 64;
+            if (smemq > kMaxSmem) return FVAE_ERR_LIMIT;
+            if ((ce2 = cudaFuncSetAttribute(tc_q_from_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemq))) != cudaSuccess) return int(ce2);
+            tc_q_from_tiles_kernel<2><<<grid, NTH, smemq, st>>>(a); count_launch();
+        }
+        if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
     }
     {   // dWih from the u tiles saved by the forward kernel (the panel is not touched)
         const size_t per_stage = size_t(NC / 8) * TILE_CH + A_BYTES;
@@ -611,7 +615,6 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         }
         if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
     }
-    (void)smem1; (void)pf1;
     PostArgs p{d.C, d.H, NC, w.ln_w, w.ln_b, w.W1, ws.q, ws.dwih, gr};
     tc_post_kernel<<<64, 256, 0, st>>>(p); count_launch();
     return int(cudaGetLastError());

@@ -1,10 +1,12 @@
 // Item kernels of the tensor-core FeatureExtractor (included by fe_tc.cu inside namespace fvae::<anon>):
-//   K1 tc_front_fwd_kernel : LayerNorm -> GEMM1 -> LeakyReLU -> GEMM2 -> GI tile        (reference module.py:26-30)
-//   K4 tc_front_bwd_kernel : recompute, du = dGI . W_ih, dpre, weight-gradient GEMMs    (autograd of the same)
+//   K1  tc_front_fwd_kernel    : LayerNorm -> GEMM1 -> LeakyReLU -> GEMM2 -> GI tile      (reference module.py:26-30);
+//                                also saves the xhat / u operand tiles and the LeakyReLU' sign bits for backward
+//   K4a tc_q_from_tiles_kernel : du = dGI . W_ih, dpre = du * LeakyReLU', Q += dpre^T [xhat | 1]   (streams saved tiles)
+//   K4b tc_wih_from_u_kernel   : dWih += dGI^T [u | 1]                                             (streams saved tiles)
 // An item is (sequence tile of 128 stocks, time step): 128 panel rows = one UMMA M = the 128 TMEM lanes.
-// 512 threads per CTA: thread (row = tid & 127, part = tid >> 7) owns 40 of the 160 columns of its row in
+// K1 runs 512 threads per CTA: thread (row = tid & 127, part = tid >> 7) owns 40 of the 160 columns of its row in
 // LayerNorm and in every epilogue (warps w, w+4, w+8, w+12 read the same 32 TMEM lanes, different columns);
-// 16 resident warps hide the LDS / TMEM-load / MUFU latencies that 4 warps cannot.
+// 16 resident warps hide the LDS / TMEM-load latencies that 4 warps cannot.
 #pragma once
 
 struct ItemArgs {
@@ -360,6 +362,14 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
             mma_commit(&bars[1]);
         }
     };
+    // my 5 chunks of the xhat tile -> HBM (saved for backward); reads what this thread itself wrote
+    auto save_xhat = [&](int64_t item) {
+        unsigned char* g = reinterpret_cast<unsigned char*>(a.ws.xh) + size_t(item) * A_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < HALF_CH; ++ch)
+            *reinterpret_cast<uint4*>(g + tile_off(TM, row, HALF_CH * half + ch)) =
+                *reinterpret_cast<const uint4*>(sA1 + tile_off(TM, row, HALF_CH * half + ch));
+    };
     const int64_t G = gridDim.x;
     uint32_t phase = 0;
     if (prefetch) {
@@ -369,6 +379,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
         if (item < nitems) {
             issue_item_loads<XT>(a, item, sStage, 0);
             stage_and_normalize<XT>(a, item, sStage, sA1, sStat, true);
+            save_xhat(item);
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -387,6 +398,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
             const int64_t nxt = item + G;
             if (nxt < nitems) {
                 stage_and_normalize<XT>(a, nxt, sStage, sA1, sStat, true);       // A1 is free: GEMM1(item) has completed
+                save_xhat(nxt);
                 fence_async_smem();
                 tc_fence_before_sync();
                 __syncthreads();
@@ -401,6 +413,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     } else {
         for (int64_t item = blockIdx.x; item < nitems; item += G, phase ^= 1) {
             stage_and_normalize<XT>(a, item, sStage, sA1, sStat, false);
+            save_xhat(item);
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -418,262 +431,6 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
             epilogue_gi(item);
             tc_fence_before_sync();
             __syncthreads();
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
-// ---- K4: front backward (weight gradients) ----------------------------------------------------------------------------
-// MODE 0: Q    += dpre^T [xhat | 1]   (dpre = (dGI . W_ih) * LeakyReLU'(pre))
-// MODE 1: dWih += dGI^T  [u | 1]
-template <typename XT, int MODE>
-__global__ void __launch_bounds__(NTH, 1) tc_front_bwd_kernel(ItemArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
-    const int C = a.C, NC = a.NC, NCH = NC / 8;
-    const int MBW = NC > 128 ? 2 : 1;
-    const uint32_t scr_chunks = (MODE == 0 || MBW == 2) ? 32u : 21u;     // MODE 1, one M block: dGI tile + over-read <= 16 chunks, stage 21
-    unsigned char* sW1 = smem;
-    unsigned char* sNext = sW1 + W1_BYTES;
-    unsigned char* sWihT = sNext;                                  // MODE 0 only: [NCH][CP][16]
-    if (MODE == 0) sNext += uint32_t(NCH) * CP * 16;
-    unsigned char* sA1 = sNext;  sNext += A_BYTES;                 // xhat tile
-    unsigned char* sA2 = sNext;                                    // MODE 1 only: u tile
-    if (MODE == 1) sNext += A_BYTES;
-    unsigned char* sScr = sNext;                                   // [raw rows ->] dGI tile -> dpre tile
-    sNext += scr_chunks * TILE_CH;
-    unsigned char* sStage = a.prefetch ? sNext : sScr;
-    if (a.prefetch) sNext += STAGE_BYTES;
-    float* sB1 = reinterpret_cast<float*>(sNext);
-    float* sStat = sB1 + CP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);  // 0: pre, 1: du, 2: wgrad
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-
-    copy_image(sW1, a.ws.w1g, W1_BYTES);
-    if (MODE == 0) copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
-    for (int i = tid; i < CP; i += NTH) sB1[i] = a.ws.b1f[i];
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    fence_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
-    const uint32_t COL_ACC = 160;          // wgrad accumulators: [160, 480)
-    const int64_t nitems = a.NT * a.T;
-    const bool prefetch = a.prefetch != 0 && sizeof(XT) == 2;
-    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
-    bool pending = false, started = false;
-    if (prefetch && int64_t(blockIdx.x) < nitems) issue_item_loads<XT>(a, blockIdx.x, sStage, 0);
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        if (pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }       // xhat / u / scratch tiles are free again
-        const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-        if (prefetch) issue_tile_load(sScr, gin, NCH, row, half);                   // dGI tile: scratch is free, rows live elsewhere
-        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, prefetch, prefetch);
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);   // pre
-            mma_commit(&bars[0]);
-        }
-        if (!prefetch) issue_tile_load(sScr, gin, NCH, row, half);                  // the raw rows in scratch are dead now
-        const bool more = prefetch && item + gridDim.x < nitems;
-        if (more) issue_item_loads<XT>(a, item + gridDim.x, sStage, 0);
-        mbar_wait(&bars[0], ph0);
-        ph0 ^= 1;
-        tc_fence_after_sync();
-        if (MODE == 1) {
-            epilogue_u(tmem, lane_base, half, row, C, sA2);
-            if (more) cp_async_wait<1>(); else cp_async_wait<0>();                  // the dGI tile has landed
-            fence_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                for (int mb = 0; mb < MBW; ++mb)
-                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA2), CP, started);
-                mma_commit(&bars[2]);
-            }
-        } else {
-            // LeakyReLU' mask of my 40 columns
-            uint32_t mask[2] = {0u, 0u};
-#pragma unroll
-            for (int ch = 0; ch < HALF_CH; ++ch) {
-                const int n0 = HALF_COLS * half + ch * 8;
-                float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, n0), v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int b = ch * 8 + e;
-                    if (v[e] > 0.f) mask[b >> 5] |= 1u << (b & 31);
-                }
-            }
-            if (more) cp_async_wait<1>(); else cp_async_wait<0>();                  // the dGI tile has landed
-            fence_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                issue_row_gemm(tmem, 0, smem_u32(sScr), smem_u32(sWihT), CP, CP, NC / 16);     // du = dGI . W_ih
-                mma_commit(&bars[1]);
-            }
-            mbar_wait(&bars[1], ph1);
-            ph1 ^= 1;
-            tc_fence_after_sync();
-            // dpre = du * LeakyReLU'(pre) -> bf16 tile over the (dead) dGI tile
-#pragma unroll
-            for (int ch = 0; ch < HALF_CH; ++ch) {
-                const int n0 = HALF_COLS * half + ch * 8;
-                float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, n0), v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int b = ch * 8 + e;
-                    v[e] *= ((mask[b >> 5] >> (b & 31)) & 1u) ? 1.f : kLeakySlope;
-                }
-                *reinterpret_cast<uint4*>(sScr + tile_off(TM, row, HALF_CH * half + ch)) =
-                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
-            fence_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                for (int mb = 0; mb < 2; ++mb)
-                    issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(sScr), 16 * mb, smem_u32(sA1), CP, started);
-                mma_commit(&bars[2]);
-            }
-        }
-        started = true;
-        pending = true;
-    }
-    if (pending) mbar_wait(&bars[2], ph2);
-    tc_fence_after_sync();
-    if (started) {
-        float* outbuf = MODE == 0 ? a.ws.q : a.ws.dwih;
-        const int nblk = MODE == 0 ? 2 : MBW;
-        for (int mb = 0; mb < nblk; ++mb) {
-            const int orow = mb * 128 + row;
-            const bool ok = MODE == 0 ? orow < C : orow < NC;
-            for (int ch = 0; ch < HALF_CH; ++ch) {
-                const int n0 = HALF_COLS * half + ch * 8;
-                float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + n0), v);
-                if (ok) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) atomicAdd(outbuf + size_t(orow) * CP + n0 + e, v[e]);
-                }
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
-// ---- K4b pipelined: dWih += dGI^T [u | 1] with the K1 software pipeline (dedicated row stage, two dGI buffers) -----------
-template <typename XT>
-__global__ void __launch_bounds__(NTH, 1) tc_front_bwd_wih_pipe_kernel(ItemArgs a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
-    const int C = a.C, NC = a.NC, NCH = NC / 8;
-    const int MBW = NC > 128 ? 2 : 1;
-    unsigned char* sW1 = smem;
-    unsigned char* sA1 = sW1 + W1_BYTES;                  // xhat tile
-    unsigned char* sA2 = sA1 + A_BYTES;                   // u tile
-    unsigned char* sG = sA2 + A_BYTES;                    // two dGI tiles; the M-block over-read of the second runs into the stage
-    unsigned char* sStage = sG + 2u * NCH * TILE_CH;
-    float* sB1 = reinterpret_cast<float*>(sStage + STAGE_BYTES);
-    float* sStat = sB1 + CP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);   // 0: pre, 1: wgrad
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-
-    copy_image(sW1, a.ws.w1g, W1_BYTES);
-    for (int i = tid; i < CP; i += NTH) sB1[i] = a.ws.b1f[i];
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    fence_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
-    const uint32_t COL_ACC = 160;
-    const int64_t nitems = a.NT * a.T, G = gridDim.x;
-    auto gi_tile = [&](int64_t item) { return reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH; };
-    auto issue_gemm1 = [&]() {
-        if (tid == 0) {
-            tc_fence_after_sync();
-            issue_row_gemm(tmem, 0, smem_u32(sA1), smem_u32(sW1), CP, CP, KCH / 2);
-            mma_commit(&bars[0]);
-        }
-    };
-    uint32_t ph0 = 0, ph1 = 0;
-    bool pending = false, started = false;
-    int64_t item = blockIdx.x;
-    if (item < nitems) {
-        issue_item_loads<XT>(a, item, sStage, 0);
-        issue_tile_load(sG, gi_tile(item), NCH, row, half);
-        stage_and_normalize<XT>(a, item, sStage, sA1, sStat, true, true);
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        issue_gemm1();
-        if (item + G < nitems) issue_item_loads<XT>(a, item + G, sStage, 0);
-    }
-    for (int k = 0; item < nitems; item += G, ++k) {
-        const int64_t nxt = item + G;
-        unsigned char* gcur = sG + uint32_t(k & 1) * NCH * TILE_CH;
-        unsigned char* gnext = sG + uint32_t((k & 1) ^ 1) * NCH * TILE_CH;
-        mbar_wait(&bars[0], ph0);
-        ph0 ^= 1;
-        tc_fence_after_sync();
-        if (pending) { mbar_wait(&bars[1], ph1); ph1 ^= 1; pending = false; }     // u tile and the other dGI buffer are free
-        if (nxt < nitems) issue_tile_load(gnext, gi_tile(nxt), NCH, row, half);   // lands during this item's wgrad + LayerNorm(nxt)
-        epilogue_u(tmem, lane_base, half, row, C, sA2);
-        // dGI(item) landed: it is older than rows(nxt) [issued last iteration] only for k == 0; in steady state the
-        // groups in flight are rows(nxt), dGI(nxt) -> everything older (incl. dGI(item)) completed in LayerNorm's wait
-        if (k == 0) { if (nxt < nitems) cp_async_wait<2>(); else cp_async_wait<0>(); }
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            for (int mb = 0; mb < MBW; ++mb)
-                issue_wgrad(tmem, COL_ACC + mb * CP, smem_u32(gcur), 16 * mb, smem_u32(sA2), CP, started);
-            mma_commit(&bars[1]);
-        }
-        started = true;
-        pending = true;
-        if (nxt < nitems) {
-            stage_and_normalize<XT>(a, nxt, sStage, sA1, sStat, true, false);      // waits for rows(nxt) and dGI(nxt)
-            fence_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            issue_gemm1();
-            if (nxt + G < nitems) issue_item_loads<XT>(a, nxt + G, sStage, 0);
-        }
-    }
-    if (pending) mbar_wait(&bars[1], ph1);
-    tc_fence_after_sync();
-    if (started) {
-        for (int mb = 0; mb < MBW; ++mb) {
-            const int orow = mb * 128 + row;
-            const bool ok = orow < NC;
-            for (int ch = 0; ch < HALF_CH; ++ch) {
-                const int n0 = HALF_COLS * half + ch * 8;
-                float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, COL_ACC + mb * CP + n0), v);
-                if (ok) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) atomicAdd(a.ws.dwih + size_t(orow) * CP + n0 + e, v[e]);
-                }
-            }
         }
     }
     tc_fence_before_sync();
@@ -763,67 +520,24 @@ __global__ void __launch_bounds__(WIH_THREADS, 1) tc_wih_from_u_kernel(ItemArgs 
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// ---- K4a: Q += dpre^T [xhat | 1] without recomputing GEMM 1 ------------------------------------------------------------
-// The LeakyReLU' sign bits were saved by K1, so backward needs xhat (LayerNorm of the raw rows), du = dGI . W_ih and the
-// weight-gradient MMAs only.  Software pipeline per item k:
-//     MMA du(k)  ||  LayerNorm(k+1) in registers      ->  dpre epilogue  ->  MMA Q(k)  ->  xhat(k+1) stored, loads of k+2
-// Q is kept in three TMEM blocks so that no operand tile is over-read:  A: rows o<128 (A = dpre, B = xhat, N = 160);
-// B0/B1: rows o in [128,160) computed transposed (A = xhat M-blocks, B = dpre chunks 16..19, N = 32).
-template <typename XT>
-__device__ __forceinline__ void layernorm_regs(const ItemArgs& a, int64_t st, int t, const unsigned char* stage, float* sStat,
-                                               float (&v)[HALF_COLS]) {
-    static_assert(sizeof(XT) == 2, "single-pass staging only");
-    const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7, C = a.C;
-    const int c0 = HALF_COLS * half;
-    const bool partial = c0 + HALF_COLS > C;
-    const int64_t s = st * TM + row;
-    const uint32_t off = s < a.S ? uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u) : 0u;
-    fetch_half(static_cast<const XT*>(nullptr), stage + size_t(row) * slot_bytes<XT>(C), off, half, v);
-    if (partial) {
-#pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = 0.f;
-    }
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < HALF_COLS; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
-    sStat[half * TM + row] = s1;
-    sStat[NSPLIT * TM + half * TM + row] = s2;
-    __syncthreads();
-    const float inv_c = 1.f / float(C);
-    const float mean = (sStat[row] + sStat[TM + row] + sStat[2 * TM + row] + sStat[3 * TM + row]) * inv_c;
-    const float ex2 = (sStat[4 * TM + row] + sStat[5 * TM + row] + sStat[6 * TM + row] + sStat[7 * TM + row]) * inv_c;
-    const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + kLnEps);
-    const float shift = -mean * rstd;
-#pragma unroll
-    for (int j = 0; j < HALF_COLS; ++j) v[j] = fmaf(v[j], rstd, shift);
-    if (partial) {
-#pragma unroll
-        for (int j = 0; j < HALF_COLS; ++j) if (c0 + j >= C) v[j] = (c0 + j == C) ? 1.f : 0.f;
-    }
-}
-__device__ __forceinline__ void store_xhat(const float (&v)[HALF_COLS], unsigned char* tile, int row, int half) {
-#pragma unroll
-    for (int ch = 0; ch < HALF_CH; ++ch)
-        *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
-            make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
-                       pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
-}
-
-template <typename XT>
-__global__ void __launch_bounds__(NTH, 1) tc_q_kernel(ItemArgs a) {
+// ---- K4a (streaming form): Q += dpre^T [xhat | 1] from the xhat tiles and mask bits saved by K1 ---------------------------
+// Per item two operand tiles arrive by cp.async into a ring (xhat 40 KB, dGI 20 KB); tensor work: du = dGI . W_ih,
+// then the three Q blocks; CUDA-core work: only the dpre epilogue.  MMA du(k+1) is issued right behind Q(k), so the
+// tensor pipe runs while the epilogue threads wait.
+template <int NSTG>
+__global__ void __launch_bounds__(NTH, 1) tc_q_from_tiles_kernel(ItemArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
     const int NC = a.NC, NCH = NC / 8;
-    unsigned char* sWihT = smem;                                   // [NCH][CP][16]   B of du = dGI . W_ih
-    unsigned char* sA1 = sWihT + uint32_t(NCH) * CP * 16;          // xhat tile; its M-block over-read runs into sS
-    unsigned char* sS = sA1 + A_BYTES;                             // 2 x [dGI tile -> dpre tile]
-    unsigned char* sStage = sS + 2 * A_BYTES;
-    float* sStat = reinterpret_cast<float*>(sStage + STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);      // 0: du, 1: Q
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const uint32_t g_bytes = uint32_t(NCH) * TILE_CH;
+    constexpr uint32_t STG = 2 * A_BYTES;                          // [xhat tile | dGI -> dpre tile]; xhat's M-block over-read runs into the dGI tile
+    unsigned char* sWihT = smem;
+    unsigned char* sRing = sWihT + uint32_t(NCH) * CP * 16;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + NSTG * STG);          // [0]: du, [1 + stage]: Q of that stage
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + NSTG);
     copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
-    for (uint32_t i = tid; i < 2 * A_BYTES / 16; i += NTH) reinterpret_cast<uint4*>(sS)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    for (uint32_t i = tid; i < NSTG * STG / 16; i += NTH) reinterpret_cast<uint4*>(sRing)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { for (int i = 0; i < 1 + NSTG; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     fence_async_smem();
     tc_fence_before_sync();
@@ -833,47 +547,49 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_kernel(ItemArgs a) {
     const uint32_t lane_base = uint32_t(warp & 3) * 32u;
     constexpr uint32_t COL_DU = 0, COL_QA = 160, COL_QB0 = 320, COL_QB1 = 352;
     const int64_t nitems = a.NT * a.T, G = gridDim.x;
-    auto gi_tile = [&](int64_t it) { return reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(it) * NCH * TILE_CH; };
-    auto commit_rows = [&](int64_t it) { if (it < nitems) issue_item_loads<XT>(a, it, sStage, 0); else cp_async_commit(); };
-    auto commit_dgi = [&](int64_t it, int b) { if (it < nitems) issue_tile_load(sS + uint32_t(b) * A_BYTES, gi_tile(it), NCH, row, half); else cp_async_commit(); };
-    uint32_t ph0 = 0, ph1 = 0;
-    bool started = false;
-    int64_t item = blockIdx.x;
-    float v[HALF_COLS];
-    if (item < nitems) {
-        commit_rows(item);
-        commit_dgi(item, 0);
-        cp_async_wait<1>();                       // rows(item)
-        __syncthreads();
-        layernorm_regs<XT>(a, item / a.T, int(item % a.T), sStage, sStat, v);
-        store_xhat(v, sA1, row, half);
-        __syncthreads();                          // every thread is done with the stage
-        commit_rows(item + G);
-        commit_dgi(item + G, 1);
-    }
-    for (int k = 0; item < nitems; item += G, ++k) {
-        const int b = k & 1;
-        const int64_t nxt = item + G;
-        unsigned char* sD = sS + uint32_t(b) * A_BYTES;
-        const unsigned long long mbits = a.ws.mask[size_t(item) * 4 * TM + half * TM + row];
-        cp_async_wait<2>();                       // dGI(item) has landed (rows(nxt), dGI(nxt) may still fly)
-        fence_async_smem();                       // also publishes xhat(item)
-        tc_fence_before_sync();
-        __syncthreads();
+    auto issue_loads = [&](int64_t it, int stg) {
+        if (it < nitems) {
+            unsigned char* dst = sRing + uint32_t(stg) * STG;
+            const unsigned char* xs = reinterpret_cast<const unsigned char*>(a.ws.xh) + size_t(it) * A_BYTES;
+            const unsigned char* gs = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(it) * g_bytes;
+            for (uint32_t i = tid; i < A_BYTES / 16; i += NTH) cp_async16(smem_u32(dst + i * 16), xs + i * 16);
+            for (uint32_t i = tid; i < g_bytes / 16; i += NTH) cp_async16(smem_u32(dst + A_BYTES + i * 16), gs + i * 16);
+        }
+        cp_async_commit();
+    };
+    auto issue_du = [&](int stg) {
         if (tid == 0) {
             tc_fence_after_sync();
-            issue_row_gemm(tmem, COL_DU, smem_u32(sD), smem_u32(sWihT), CP, CP, NC / 16);       // du = dGI . W_ih
+            issue_row_gemm(tmem, COL_DU, smem_u32(sRing + uint32_t(stg) * STG + A_BYTES), smem_u32(sWihT), CP, CP, NC / 16);
             mma_commit(&bars[0]);
         }
-        if (nxt < nitems) {                       // LayerNorm(nxt) in registers while the MMA runs
-            cp_async_wait<1>();                   // rows(nxt)
-            __syncthreads();
-            layernorm_regs<XT>(a, nxt / a.T, int(nxt % a.T), sStage, sStat, v);
-        }
-        mbar_wait(&bars[0], ph0);
-        ph0 ^= 1;
+    };
+    int64_t next_load = blockIdx.x;
+    for (int sidx = 0; sidx < NSTG - 1; ++sidx) { issue_loads(next_load, sidx); next_load += G; }
+    uint32_t ph_du = 0, ph_q = 0;          // ph_q: one bit per stage
+    bool started = false;
+    int k = 0;
+    int64_t item = blockIdx.x;
+    if (item < nitems) {
+        cp_async_wait<NSTG - 2>();         // loads of item 0
+        fence_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        issue_du(0);
+    }
+    for (; item < nitems; item += G, ++k) {
+        const int stg = k % NSTG;
+        unsigned char* sX = sRing + uint32_t(stg) * STG;
+        unsigned char* sD = sX + A_BYTES;
+        const unsigned long long mbits = a.ws.mask[size_t(item) * 4 * TM + half * TM + row];
+        // refill the stage item k-1 used (its Q MMAs were committed one iteration ago)
+        const int refill = (k + NSTG - 1) % NSTG;
+        if (k > 0) { mbar_wait(&bars[1 + refill], (ph_q >> refill) & 1u); ph_q ^= 1u << refill; }
+        issue_loads(next_load, refill);
+        next_load += G;
+        mbar_wait(&bars[0], ph_du);        // du(k) is in TMEM
+        ph_du ^= 1;
         tc_fence_after_sync();
-        // dpre = du * LeakyReLU'(pre) -> bf16 tile over the dead dGI tile
 #pragma unroll
         for (int ch = 0; ch < HALF_CH; ++ch) {
             float d[8];
@@ -883,30 +599,26 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_kernel(ItemArgs a) {
             *reinterpret_cast<uint4*>(sD + tile_off(TM, row, HALF_CH * half + ch)) =
                 make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
         }
+        const bool has_next = item + G < nitems;
+        if (has_next) cp_async_wait<NSTG - 2>(); else cp_async_wait<0>();     // loads of item k+1 (needed by du(k+1) below)
         fence_async_smem();
         tc_fence_before_sync();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after_sync();
-            issue_wgrad(tmem, COL_QA, smem_u32(sD), 0, smem_u32(sA1), CP, started);                       // rows o < 128
-            issue_wgrad(tmem, COL_QB0, smem_u32(sA1), 0, smem_u32(sD) + 16 * TILE_CH, 32, started);      // rows o >= 128, i < 128
-            issue_wgrad(tmem, COL_QB1, smem_u32(sA1), 16, smem_u32(sD) + 16 * TILE_CH, 32, started);     // rows o >= 128, i >= 128
-            mma_commit(&bars[1]);
+            issue_wgrad(tmem, COL_QA, smem_u32(sD), 0, smem_u32(sX), CP, started);                       // rows o < 128
+            issue_wgrad(tmem, COL_QB0, smem_u32(sX), 0, smem_u32(sD) + 16 * TILE_CH, 32, started);      // rows o >= 128, i < 128
+            issue_wgrad(tmem, COL_QB1, smem_u32(sX), 16, smem_u32(sD) + 16 * TILE_CH, 32, started);     // rows o >= 128, i >= 128
+            mma_commit(&bars[1 + stg]);
         }
         started = true;
-        mbar_wait(&bars[1], ph1);                 // xhat tile and this dGI/dpre buffer are free again
-        ph1 ^= 1;
-        tc_fence_after_sync();
-        if (nxt < nitems) store_xhat(v, sA1, row, half);
-        __syncthreads();                          // LayerNorm(nxt) no longer needs the stage (all threads passed it)
-        commit_rows(nxt + G);
-        commit_dgi(nxt + G, b);
+        if (has_next) issue_du((k + 1) % NSTG);       // queued right behind Q(k): COL_DU was fully read before the barrier above
     }
+    if (k > 0) { const int last = (k - 1) % NSTG; mbar_wait(&bars[1 + last], (ph_q >> last) & 1u); }
     cp_async_wait<0>();
     tc_fence_after_sync();
     if (started) {
         const int C = a.C;
-        // block A: lane = o (< 128), my 40 columns i
         for (int ch = 0; ch < HALF_CH; ++ch) {
             const int n0 = HALF_COLS * half + ch * 8;
             float d[8];
@@ -916,7 +628,6 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_kernel(ItemArgs a) {
                 for (int e = 0; e < 8; ++e) atomicAdd(a.ws.q + size_t(row) * CP + n0 + e, d[e]);
             }
         }
-        // blocks B0 / B1: lane = i (B0: i = row, B1: i = 128 + row), my 8 columns o' = 8*half .. -> o = 128 + o'
         for (int blk = 0; blk < 2; ++blk) {
             float d[8];
             tmem_ld8(tmem_addr(tmem, lane_base, (blk == 0 ? COL_QB0 : COL_QB1) + 8 * half), d);
