@@ -906,26 +906,29 @@ int loss_reduce(const float* date_loss, int B, float* loss, cudaStream_t stream)
     return int(cudaGetLastError());
 }
 
+// padded hidden width: the sweeps cost HP FMAs per (stock, weight row), so pad H as little as possible
+static int pick_hp(int H) { return H <= 20 ? 20 : (H <= 32 ? 32 : (H <= 48 ? 48 : 64)); }
+
 int heads_forward(const HeadsArgs& a, cudaStream_t stream) {
-    const int HP = a.H <= 32 ? 32 : 64;
+    const int HP = pick_hp(a.H);
     const size_t smem = fwd_smem_bytes(HP, a.H, a.K, a.M);
     int rc;
-    if (HP == 32) {
-        if ((rc = set_smem(heads_fwd_kernel<32>, smem)) != 0) return rc;
-        heads_fwd_kernel<32><<<a.B, NT, smem, stream>>>(a); count_launch();
-    } else {
-        if ((rc = set_smem(heads_fwd_kernel<64>, smem)) != 0) return rc;
-        heads_fwd_kernel<64><<<a.B, NT, smem, stream>>>(a); count_launch();
-    }
+#define FVAE_LAUNCH_FWD(HPV)                                                        \
+    do {                                                                            \
+        if ((rc = set_smem(heads_fwd_kernel<HPV>, smem)) != 0) return rc;           \
+        heads_fwd_kernel<HPV><<<a.B, NT, smem, stream>>>(a); count_launch();        \
+    } while (0)
+    if (HP == 20) FVAE_LAUNCH_FWD(20); else if (HP == 32) FVAE_LAUNCH_FWD(32); else if (HP == 48) FVAE_LAUNCH_FWD(48); else FVAE_LAUNCH_FWD(64);
+#undef FVAE_LAUNCH_FWD
     return int(cudaGetLastError());
 }
 
 int heads_backward(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t stream) {
-    const int HP = a.H <= 32 ? 32 : 64;
+    const int HP = pick_hp(a.H);
     const int NF = a.M + 2 * a.K + a.H;
     const int NB = (NF + NT - 1) / NT;
-    if (NB > 3) return FVAE_ERR_LIMIT;
-    const bool wsm = HP == 32 && bwd_smem_bytes(HP, a.H, a.K, a.M, true) <= 110 * 1024;   // keep two CTAs per SM
+    if (NB > 3 || (NB == 3 && HP != 32)) return FVAE_ERR_LIMIT;
+    const bool wsm = HP <= 32 && bwd_smem_bytes(HP, a.H, a.K, a.M, true) <= 110 * 1024;   // keep two CTAs per SM
     const size_t smem = bwd_smem_bytes(HP, a.H, a.K, a.M, wsm);
     int rc;
 #define FVAE_LAUNCH_BWD(HPV, NBV, WSMV)                                                      \
@@ -933,11 +936,16 @@ int heads_backward(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t 
         if ((rc = set_smem(heads_bwd_kernel<HPV, NBV, WSMV>, smem)) != 0) return rc;         \
         heads_bwd_kernel<HPV, NBV, WSMV><<<a.B, NT, smem, stream>>>(a, g, dE); count_launch(); \
     } while (0)
-    if (HP == 32) {
+    if (HP == 20) {
+        if (wsm) { if (NB == 1) FVAE_LAUNCH_BWD(20, 1, true); else FVAE_LAUNCH_BWD(20, 2, true); }
+        else { if (NB == 1) FVAE_LAUNCH_BWD(20, 1, false); else FVAE_LAUNCH_BWD(20, 2, false); }
+    } else if (HP == 32) {
         if (wsm) { if (NB == 1) FVAE_LAUNCH_BWD(32, 1, true); else if (NB == 2) FVAE_LAUNCH_BWD(32, 2, true); else FVAE_LAUNCH_BWD(32, 3, true); }
         else { if (NB == 1) FVAE_LAUNCH_BWD(32, 1, false); else if (NB == 2) FVAE_LAUNCH_BWD(32, 2, false); else FVAE_LAUNCH_BWD(32, 3, false); }
+    } else if (HP == 48) {
+        if (NB == 1) FVAE_LAUNCH_BWD(48, 1, false); else FVAE_LAUNCH_BWD(48, 2, false);
     } else {
-        if (NB == 1) FVAE_LAUNCH_BWD(64, 1, false); else if (NB == 2) FVAE_LAUNCH_BWD(64, 2, false); else return FVAE_ERR_LIMIT;
+        if (NB == 1) FVAE_LAUNCH_BWD(64, 1, false); else FVAE_LAUNCH_BWD(64, 2, false);
     }
 #undef FVAE_LAUNCH_BWD
     return int(cudaGetLastError());
