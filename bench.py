@@ -219,63 +219,90 @@ def main():
     ms_per_step = ms / args.steps
     value = world * S / (ms_per_step * 1e-3)
 
-    # ---- phase timing on the launching stream (FeatureExtractor chain alone), for the roofline
+    # ---- roofline of the dominant kernel, timed ALONE with CUDA events on the launching stream
+    # dominant kernel = tc_front_fwd_kernel (K1: LayerNorm -> GEMM 128x160x160 -> LeakyReLU -> GEMM 128xNCx160 per item);
+    # algorithmic work per launch: FLOPs = S*T*2*(C^2 + 3HC); bytes = one read of the bf16 panel (S*T*C*2).
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    peak_burst = float(peaks.get("bf16_tflops", 1590.0))
+    peak_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, 6.65 TB/s)"
     flops_step = S * f_fe(T, H)
-    achieved_tf = flops_step / (ms_per_step * 1e-3) / 1e12
-    fe_ms = None
-    if rank == 0:
-        e, saved = engine.fe_forward(layout, flat, x, precision)
-        de = torch.randn_like(e)
+    step_tf = flops_step / (ms_per_step * 1e-3) / 1e12
+    roofline = None
+    if rank == 0 and precision == "bf16":
+        out_k, st_k = engine.elbo_forward(layout, flat, x, y, date_ptr, train=True, precision="bf16", philox=(42, 1, unit_base))
         torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(3, args.steps // 4)
-        a0.record()
+        reps = max(5, args.steps)
+        for _ in range(3):
+            engine.rerun_front_forward(st_k)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
         for _ in range(reps):
-            e, saved = engine.fe_forward(layout, flat, x, precision)
-            engine.fe_backward(layout, saved, de)
-        a1.record()
+            engine.rerun_front_forward(st_k)
+        k1.record()
         torch.cuda.synchronize()
-        fe_ms = a0.elapsed_time(a1) / reps
-        del e, saved, de
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "peak_source": peak_src,
-                "note": "whole ELBO step (all kernels) against the dense bf16 tensor peak; algorithmic FLOPs = "
-                        "S*3*2T(C^2+3HC+3H^2) (FeatureExtractor contractions, unpadded)",
-                "fe_chain_ms": fe_ms,
-                "fe_chain_frac": (flops_step / (fe_ms * 1e-3) / 1e12 / peak_tf) if fe_ms else None,
-                "hbm_algorithmic_gbs": S * (T * C_FEATURES * (2 if args.panel == "bf16" else 4) + 4) / (ms_per_step * 1e-3) / 1e9}
+        k_ms = k0.elapsed_time(k1) / reps
+        k_flops = S * T * 2.0 * (C_FEATURES * C_FEATURES + 3 * H * C_FEATURES)
+        k_bytes = S * T * C_FEATURES * (2 if args.panel == "bf16" else 4)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        ach = k_flops / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "tc_front_fwd_kernel", "achieved": ach, "peak": peak_burst, "unit": "TFLOP/s",
+                    "frac": ach / peak_burst, "traffic": traffic, "peak_source": peak_src + ", burst figure (kernel timed alone)",
+                    "kernel_ms": k_ms, "algorithmic_flops_per_launch": k_flops, "algorithmic_bytes_per_launch": k_bytes,
+                    "hbm_algorithmic_gbs": k_bytes / (k_ms * 1e-3) / 1e9, "hbm_frac_algorithmic": k_bytes / (k_ms * 1e-3) / 1e9 / peak_hbm,
+                    "step": {"achieved": step_tf, "peak": peak_sust, "frac": step_tf / peak_sust,
+                             "note": "whole ELBO step (all kernels): S*3*2T(C^2+3HC+3H^2) algorithmic FLOPs / step time vs sustained bf16 peak"}}
+        del out_k, st_k
+    elif rank == 0:
+        roofline = {"bound": "tensor", "kernel": "whole step (fp32 CUDA-core mode)", "achieved": step_tf, "peak": peak_sust,
+                    "unit": "TFLOP/s", "frac": step_tf / peak_sust, "traffic": None, "peak_source": peak_src}
 
-    # ---- end to end through the host-buffer entry (pinned fp32 host panel as the reference's loader yields)
+    # ---- end to end through the host-buffer entry: pinned host panel -> H2D -> step -> D2H of the loss, every step.
+    # Primary number: fp32 host panel (what the reference's loader yields, train_model.py:23); the H2D copy of step i+1
+    # overlaps the compute of step i.  Secondary: the same with the panel kept in bf16 on the host.
     e2e = None
     if not args.no_e2e:
-        xh = x.float().to("cpu").pin_memory()      # fp32 host panel, as the reference loader yields (train_model.py:23)
-        yh = y.to("cpu").pin_memory()
         ph = date_ptr.to("cpu").pin_memory()
-        for _ in range(3):
-            stepper.step_from_host(xh, yh, ph, global_dates=B * world, unit_base=unit_base, train=True)
-        barrier()
+        yh = y.to("cpu").pin_memory()
         n_e2e = max(3, args.steps // 2)
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(n_e2e):
-            stepper.step_from_host(xh, yh, ph, global_dates=B * world, unit_base=unit_base, train=True)
-        b1.record()
-        barrier()
-        t2 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t2.item()) / n_e2e
-        e2e = {"value": world * S / (e2e_ms * 1e-3), "unit": "date*stocks/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": xh.numel() * xh.element_size() + yh.numel() * 4 + ph.numel() * 4,
-               "d2h_bytes_per_step": 4, "host_panel_dtype": str(xh.dtype).replace("torch.", "")}
-        del xh, yh
+        kw = dict(global_dates=B * world, unit_base=unit_base, train=True)
+
+        def run_e2e(xh):
+            for _ in stepper.run_from_host([(xh, yh, ph)] * 3, **kw):
+                pass
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in stepper.run_from_host([(xh, yh, ph)] * n_e2e, **kw):
+                pass
+            b1.record()
+            barrier()
+            t2 = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            return float(t2.item()) / n_e2e
+
+        xh32 = x.float().to("cpu").pin_memory()
+        ms32 = run_e2e(xh32)
+        h2d32 = xh32.numel() * xh32.element_size() + yh.numel() * 4 + ph.numel() * 4
+        del xh32
+        xh16 = x.to(torch.bfloat16).to("cpu").pin_memory()
+        ms16 = run_e2e(xh16)
+        h2d16 = xh16.numel() * xh16.element_size() + yh.numel() * 4 + ph.numel() * 4
+        del xh16
+        e2e = {"value": world * S / (ms32 * 1e-3), "unit": "date*stocks/s", "ms_per_step": ms32, "h2d_bytes_per_step": h2d32,
+               "d2h_bytes_per_step": 4, "host_panel_dtype": "float32", "h2d_gbs": h2d32 / (ms32 * 1e-3) / 1e9,
+               "overlap": "H2D of step i+1 on a copy stream under the compute of step i",
+               "bf16_host_panel": {"value": world * S / (ms16 * 1e-3), "ms_per_step": ms16, "h2d_bytes_per_step": h2d16}}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

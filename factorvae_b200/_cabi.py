@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
     L.fvae_fe_forward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i32, vp, vp, i64, vp]
     L.fvae_fe_backward.restype = C.c_int
     L.fvae_fe_backward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i32, vp, vp, vp, i64, vp]
+    L.fvae_debug_front_forward.restype = C.c_int
+    L.fvae_debug_front_forward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i64, vp]
     L.fvae_workspace_latent.restype = vp
     L.fvae_workspace_latent.argtypes = [C.POINTER(Shape), i32, vp]
     if L.fvae_abi_version() != 1:
@@ -85,7 +87,7 @@ def lib() -> C.CDLL:
     return L
 
 
-EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
+EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_debug_front_forward", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
            "fvae_elbo_forward", "fvae_elbo_backward", "fvae_predict", "fvae_fe_forward", "fvae_fe_backward",
            "fvae_workspace_latent"]
 

@@ -85,6 +85,53 @@ class DateShardedStep:
         out, st = self.step(self._dev["x"], self._dev["y"], self._dev["date_ptr"], **kw)
         return float(self.loss.item()), out, st
 
+    def run_from_host(self, batches, **kw):
+        """Pipelined end-to-end loop: yields the loss (Python float) of every batch of `batches`, an iterable of
+        pinned HOST tuples (x, y, date_ptr).  The H2D copy of batch i+1 runs on a copy stream while batch i computes,
+        so a step costs max(copy, compute) instead of their sum; every batch is still copied and its loss read back."""
+        dev = self.flat.device
+        compute = torch.cuda.current_stream(dev)
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(dev)
+        bufs = [dict(), dict()]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def enqueue_copy(slot, batch):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])           # the step that last read this slot has finished
+                for name, src in zip(("x", "y", "date_ptr"), batch):
+                    buf = bufs[slot].get(name)
+                    if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+                        buf = torch.empty(src.shape, dtype=src.dtype, device=dev)
+                        bufs[slot][name] = buf
+                    buf.copy_(src, non_blocking=True)
+                copied[slot].record(copy_stream)
+
+        it = iter(batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        consumed[0].record(compute)
+        consumed[1].record(compute)
+        enqueue_copy(0, nxt)
+        slot = 0
+        while nxt is not None:
+            try:
+                following = next(it)
+            except StopIteration:
+                following = None
+            if following is not None:
+                enqueue_copy(slot ^ 1, following)
+            compute.wait_event(copied[slot])
+            b = bufs[slot]
+            self.step(b["x"], b["y"], b["date_ptr"], **kw)
+            consumed[slot].record(compute)
+            yield float(self.loss.item())                       # D2H read of this step's result
+            nxt, slot = following, slot ^ 1
+
     def assign_grads(self, model) -> None:
         """Expose the flat gradient as `.grad` of the model's parameters (views, no copy)."""
         for name, p in model.named_parameters():

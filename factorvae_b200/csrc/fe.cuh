@@ -29,6 +29,7 @@ int fe_f32_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const Fe
 int64_t fe_tc_workspace_bytes(const FeDims& d);
 int fe_tc_supported(const FeDims& d);
 int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, void* ws, cudaStream_t stream);
+int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* ws, cudaStream_t stream);   // diagnostics: K1 alone
 int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG& g, const float* dE, void* ws,
                    cudaStream_t stream);
 

@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
     float* sBhn = reinterpret_cast<float*>(sDgh + uint32_t(16 * MB) * TILE_CH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBhn + HP);      // 0: gh, 1: dh, 2: dW
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-    const uint32_t COL_DH = uint32_t(NC), COL_DW = uint32_t(NC + HP);
+    // the dh accumulator aliases the first HP columns of the gh accumulator (gh is dead once the gate epilogue has run)
+    const uint32_t COL_DH = 0u, COL_DW = uint32_t(NC);
     copy_image(sWhh, a.ws.whh, uint32_t(HCH) * NC * 16);
     copy_image(sWhhT, a.ws.whhT, uint32_t(NCH) * HP * 16);
     for (uint32_t i = tid; i < uint32_t(16 * MB) * TILE_CH / 16; i += TM) reinterpret_cast<uint4*>(sDgh)[i] = make_uint4(0, 0, 0, 0);
@@ -534,6 +535,23 @@ int fe_tc_supported(const FeDims& d) {
 
 int64_t fe_tc_workspace_bytes(const FeDims& d) { return carve_tc(d, nullptr).bytes; }
 
+// K1 alone (the operand images must already be in the workspace): used by fe_tc_forward and by bench.py's
+// per-kernel roofline timing through fvae_debug_front_forward.
+int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream_t st) {
+    TcWs ws = carve_tc(d, wsp);
+    const int NC = nc_of(d.H);
+    ItemArgs a = make_item_args(d, x, ws);
+    const int nsm = num_sms();
+    const int64_t nitems = a.NT * d.T;
+    const int grid = int(nitems < nsm ? nitems : nsm);
+    const size_t tail = (CP + NC + 2 * NSPLIT * TM) * 4 + 64;
+    const size_t with_stage = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + STAGE_BYTES + tail;
+    a.prefetch = (x.dtype == FVAE_BF16 && with_stage <= kMaxSmem) ? 1 : 0;
+    const size_t smem = a.prefetch ? with_stage : W1_BYTES + size_t(KCH) * NC * 16 + A_BYTES + STAGE_BYTES + tail;
+    if (x.dtype == FVAE_BF16) return launch_smem(tc_front_fwd_kernel<__nv_bfloat16>, grid, smem, st, a);
+    return launch_smem(tc_front_fwd_kernel<float>, grid, smem, st, a);
+}
+
 int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, void* wsp, cudaStream_t st) {
     TcWs ws = carve_tc(d, wsp);
     const int NC = nc_of(d.H), HP = hp_of(d.H), NB = nb8_of(d.H);
@@ -541,18 +559,8 @@ int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, 
     tc_prep_kernel<<<64, 256, 0, st>>>(p); count_launch();
     ItemArgs a = make_item_args(d, x, ws);
     const int nsm = num_sms();
-    const int64_t nitems = a.NT * d.T;
     int rc;
-    {
-        const int grid = int(nitems < nsm ? nitems : nsm);
-        const size_t tail = (CP + NC + 2 * NSPLIT * TM) * 4 + 64;
-        const size_t with_stage = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + STAGE_BYTES + tail;
-        a.prefetch = (x.dtype == FVAE_BF16 && with_stage <= kMaxSmem) ? 1 : 0;
-        const size_t smem = a.prefetch ? with_stage : W1_BYTES + size_t(KCH) * NC * 16 + A_BYTES + STAGE_BYTES + tail;
-        if (x.dtype == FVAE_BF16) rc = launch_smem(tc_front_fwd_kernel<__nv_bfloat16>, grid, smem, st, a);
-        else rc = launch_smem(tc_front_fwd_kernel<float>, grid, smem, st, a);
-        if (rc != 0) return rc;
-    }
+    if ((rc = fe_tc_front_only(d, x, wsp, st)) != 0) return rc;
     GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, e, nullptr, nullptr, nullptr};
     const size_t smem = size_t(HP / 8) * NC * 16 + size_t(HP / 8) * TILE_CH + HP * 4 + 64;
     const int ctas_per_sm = NC <= 128 ? 4 : 2;
@@ -572,10 +580,12 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, nullptr, dE, gr.Whh, gr.bhh};
         const int MB = NC > 128 ? 2 : 1;
         const size_t smem = size_t(HP / 8) * NC * 16 + size_t(NC / 8) * HP * 16 + size_t(HP / 8) * TILE_CH + size_t(16 * MB) * TILE_CH + HP * 4 + 64;
-        const uint32_t cols = uint32_t(NC + HP + MB * HP);
-        const int ctas_per_sm = cols <= 256 ? 2 : 1;
+        const uint32_t cols = uint32_t(NC + MB * HP);
+        int ctas_per_sm = cols <= 128 ? 4 : (cols <= 256 ? 2 : 1);
+        while (ctas_per_sm > 1 && smem * ctas_per_sm > kMaxSmem) ctas_per_sm >>= 1;
         const int grid = int(a.NT < int64_t(nsm) * ctas_per_sm ? a.NT : int64_t(nsm) * ctas_per_sm);
-        if (cols <= 256) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 256>, grid, smem, st, g)); }
+        if (cols <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 128>, grid, smem, st, g)); }
+        else if (cols <= 256) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 256>, grid, smem, st, g)); }
         else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 512>, grid, smem, st, g)); }
         if (rc != 0) return rc;
     }

@@ -286,6 +286,17 @@ int fvae_fe_backward(const fvae_shape* shape, const fvae_panel* x, const float* 
     return fe_backward_any(fd, *x, fw, fg, precision, de, W.fe_ws, static_cast<cudaStream_t>(stream));
 }
 
+int fvae_debug_front_forward(const fvae_shape* shape, const fvae_panel* x, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc;
+    if ((rc = check_shape(shape, FVAE_PREC_BF16_TC)) != 0) return rc;
+    if ((rc = check_panel(x, shape)) != 0) return rc;
+    if (!workspace) return FVAE_ERR_NULL;
+    Workspace W = carve(*shape, FVAE_PREC_BF16_TC, workspace);
+    if (W.bytes > workspace_bytes) return FVAE_ERR_WORKSPACE;
+    const FeDims fd{shape->S, shape->T, shape->C, shape->H};
+    return fe_tc_front_only(fd, *x, W.fe_ws, static_cast<cudaStream_t>(stream));
+}
+
 const float* fvae_workspace_latent(const fvae_shape* shape, int32_t precision, const void* workspace) {
     if (check_shape(shape, precision) != 0 || !workspace) return nullptr;
     return carve(*shape, precision, const_cast<void*>(workspace)).e;

@@ -229,6 +229,13 @@ def elbo_backward(layout: ParamLayout, st: StepState, grad: Optional[torch.Tenso
     return grad
 
 
+def rerun_front_forward(st: StepState) -> None:
+    """Diagnostics: launch only the dominant tensor-core kernel again on the state of a bf16 forward (bench.py)."""
+    rc = _cabi.lib().fvae_debug_front_forward(C.byref(st.shape), C.byref(st.panel), st.workspace.data_ptr(),
+                                              st.workspace.numel(), _stream())
+    _cabi.check(rc, "fvae_debug_front_forward")
+
+
 def latent(st: StepState) -> torch.Tensor:
     """e = h_T (S, H) of the forward that produced `st` (a copy)."""
     L = _cabi.lib()

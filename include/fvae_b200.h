@@ -148,6 +148,12 @@ int fvae_fe_forward(const fvae_shape* shape, const fvae_panel* x, const float* p
 int fvae_fe_backward(const fvae_shape* shape, const fvae_panel* x, const float* params, int32_t precision,
                      const float* de, float* grad, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* diagnostics: re-launch ONLY the dominant tensor-core kernel (front forward: LayerNorm -> GEMM -> LeakyReLU -> GEMM)
+ * on a workspace that a previous fvae_elbo_forward(FVAE_PREC_BF16_TC) call prepared; bench.py times it with CUDA
+ * events for the per-kernel roofline. */
+int fvae_debug_front_forward(const fvae_shape* shape, const fvae_panel* x, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
 /* device e[S][H] of the last forward on this workspace (for tests / diagnostics). */
 const float* fvae_workspace_latent(const fvae_shape* shape, int32_t precision, const void* workspace);
 
