@@ -595,19 +595,21 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
     {   // Q from the saved xhat tiles / mask bits (the panel is not touched)
-        const size_t per_stage = A_BYTES + A_BYTES;          // xhat tile + [dGI -> dpre] tile
+        const size_t g_bytes = size_t(NC / 8) * TILE_CH;
+        const size_t per_stage = A_BYTES + (g_bytes > A_BYTES ? g_bytes : A_BYTES);          // xhat tile + [dGI -> dpre] tile
         const size_t wt = size_t(NC / 8) * CP * 16;
         cudaError_t ce2;
-        if (wt + 3 * per_stage + 64 <= kMaxSmem) {
-            const size_t smemq = wt + 3 * per_stage + 64;
-            if ((ce2 = cudaFuncSetAttribute(tc_q_from_tiles_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemq))) != cudaSuccess) return int(ce2);
-            tc_q_from_tiles_kernel<3><<<grid, NTH, smemq, st>>>(a); count_launch();
-        } else {
-            const size_t smemq = wt + 2 * per_stage + 64;
-            if (smemq > kMaxSmem) return FVAE_ERR_LIMIT;
-            if ((ce2 = cudaFuncSetAttribute(tc_q_from_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemq))) != cudaSuccess) return int(ce2);
-            tc_q_from_tiles_kernel<2><<<grid, NTH, smemq, st>>>(a); count_launch();
-        }
+#define FVAE_LAUNCH_Q(NSTGV)                                                                                          \
+        do {                                                                                                          \
+            const size_t smemq = wt + NSTGV * per_stage + 64;                                                         \
+            if ((ce2 = cudaFuncSetAttribute(tc_q_from_tiles_kernel<NSTGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemq))) != cudaSuccess) return int(ce2); \
+            tc_q_from_tiles_kernel<NSTGV><<<grid, NTH, smemq, st>>>(a); count_launch();                               \
+        } while (0)
+        if (wt + 3 * per_stage + 64 <= kMaxSmem) FVAE_LAUNCH_Q(3);
+        else if (wt + 2 * per_stage + 64 <= kMaxSmem) FVAE_LAUNCH_Q(2);
+        else if (wt + per_stage + 64 <= kMaxSmem) FVAE_LAUNCH_Q(1);
+        else return FVAE_ERR_LIMIT;
+#undef FVAE_LAUNCH_Q
         if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
     }
     {   // dWih from the u tiles saved by the forward kernel (the panel is not touched)

@@ -530,7 +530,10 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_from_tiles_kernel(ItemArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
     const int NC = a.NC, NCH = NC / 8;
     const uint32_t g_bytes = uint32_t(NCH) * TILE_CH;
-    constexpr uint32_t STG = 2 * A_BYTES;                          // [xhat tile | dGI -> dpre tile]; xhat's M-block over-read runs into the dGI tile
+    // stage = [xhat tile | dGI -> dpre tile]; xhat's M-block over-read runs into the dGI tile, which is the larger of
+    // the dGI tile (NC columns) and the dpre tile (160 columns)
+    const uint32_t d_bytes = g_bytes > A_BYTES ? g_bytes : A_BYTES;
+    const uint32_t STG = A_BYTES + d_bytes;
     unsigned char* sWihT = smem;
     unsigned char* sRing = sWihT + uint32_t(NCH) * CP * 16;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + NSTG * STG);          // [0]: du, [1 + stage]: Q of that stage
@@ -564,20 +567,60 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_from_tiles_kernel(ItemArgs a) {
             mma_commit(&bars[0]);
         }
     };
-    int64_t next_load = blockIdx.x;
-    for (int sidx = 0; sidx < NSTG - 1; ++sidx) { issue_loads(next_load, sidx); next_load += G; }
     uint32_t ph_du = 0, ph_q = 0;          // ph_q: one bit per stage
     bool started = false;
     int k = 0;
     int64_t item = blockIdx.x;
-    if (item < nitems) {
-        cp_async_wait<NSTG - 2>();         // loads of item 0
+    if (NSTG == 1) {
+        // both tiles and the W_ih^T image do not fit twice (NC > 160): plain serial loop
+        for (; item < nitems; item += G, ++k) {
+            unsigned char* sX = sRing;
+            unsigned char* sD = sX + A_BYTES;
+            const unsigned long long mbits = a.ws.mask[size_t(item) * 4 * TM + half * TM + row];
+            if (k > 0) { mbar_wait(&bars[1], ph_q & 1u); ph_q ^= 1u; }
+            issue_loads(item, 0);
+            cp_async_wait<0>();
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            issue_du(0);
+            mbar_wait(&bars[0], ph_du);
+            ph_du ^= 1;
+            tc_fence_after_sync();
+#pragma unroll
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                float d[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_DU + HALF_COLS * half + ch * 8), d);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[e] *= ((mbits >> (ch * 8 + e)) & 1ull) ? 1.f : kLeakySlope;
+                *reinterpret_cast<uint4*>(sD + tile_off(TM, row, HALF_CH * half + ch)) =
+                    make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+            }
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                issue_wgrad(tmem, COL_QA, smem_u32(sD), 0, smem_u32(sX), CP, started);
+                issue_wgrad(tmem, COL_QB0, smem_u32(sX), 0, smem_u32(sD) + 16 * TILE_CH, 32, started);
+                issue_wgrad(tmem, COL_QB1, smem_u32(sX), 16, smem_u32(sD) + 16 * TILE_CH, 32, started);
+                mma_commit(&bars[1]);
+            }
+            started = true;
+        }
+        if (k > 0) mbar_wait(&bars[1], ph_q & 1u);
+        k = 0;                              // the ring epilogue below must not wait again
+    }
+    int64_t next_load = blockIdx.x;
+    if (NSTG > 1) for (int sidx = 0; sidx < NSTG - 1; ++sidx) { issue_loads(next_load, sidx); next_load += G; }
+    if (NSTG > 1 && item < nitems) {
+        cp_async_wait<(NSTG >= 2 ? NSTG - 2 : 0)>();         // loads of item 0
         fence_async_smem();
         tc_fence_before_sync();
         __syncthreads();
         issue_du(0);
     }
-    for (; item < nitems; item += G, ++k) {
+    for (; NSTG > 1 && item < nitems; item += G, ++k) {
         const int stg = k % NSTG;
         unsigned char* sX = sRing + uint32_t(stg) * STG;
         unsigned char* sD = sX + A_BYTES;
@@ -600,7 +643,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_from_tiles_kernel(ItemArgs a) {
                 make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
         }
         const bool has_next = item + G < nitems;
-        if (has_next) cp_async_wait<NSTG - 2>(); else cp_async_wait<0>();     // loads of item k+1 (needed by du(k+1) below)
+        if (has_next) cp_async_wait<(NSTG >= 2 ? NSTG - 2 : 0)>(); else cp_async_wait<0>();     // loads of item k+1 (needed by du(k+1) below)
         fence_async_smem();
         tc_fence_before_sync();
         __syncthreads();

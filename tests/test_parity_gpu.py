@@ -264,7 +264,10 @@ def test_bf16_tc_latent_close_to_fp32_kernels_multi_tile(cuda_device):
 
 @pytest.mark.parametrize("shape", [dict(B=3, N=100, T=5, H=20, K=20), dict(B=2, N=100, T=4, H=48, K=48),
                                    dict(B=2, N=75, T=3, H=60, K=60), dict(B=1, N=140, T=6, H=64, K=8),
-                                   dict(B=1, N=130, T=2, H=8, K=4)])
+                                   dict(B=1, N=130, T=2, H=8, K=4),
+                                   # more items than CTAs x ring stages: exercises the cp.async rings / software pipelines
+                                   dict(B=10, N=130, T=36, H=60, K=8), dict(B=10, N=130, T=36, H=48, K=8),
+                                   dict(B=16, N=128, T=40, H=20, K=8)])
 def test_bf16_tc_chain_vs_fp32_kernels(shape, cuda_device):
     """Every tensor-core kernel (front fwd, GRU fwd, BPTT, both weight-gradient kernels, post) against the
     fp32 CUDA-core chain on multi-tile, ragged shapes; per-section diagnostics localise a broken kernel."""
