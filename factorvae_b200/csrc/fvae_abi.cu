@@ -46,6 +46,15 @@ Workspace carve(const fvae_shape& s, int precision, void* base) {
     w.sv.bad = reinterpret_cast<int*>(take(B * K * 4));
     w.sv.clamp_post = reinterpret_cast<int*>(take(B * K * 4));
     w.sv.clamp_prior = reinterpret_cast<int*>(take(B * K * 4));
+    w.sv.t_dyp = reinterpret_cast<float*>(take(B * M * 4));
+    w.sv.t_dps = reinterpret_cast<float*>(take(B * K * H * 4));
+    w.sv.t_pdp = reinterpret_cast<float*>(take(B * K * 4));
+    w.sv.t_dmuz = nullptr;
+    w.sv.t_b1 = w.sv.t_b2 = nullptr;
+    if (precision == FVAE_PREC_BF16_TC && heads_tc_supported(s.H, s.K, s.M)) {
+        w.sv.t_b1 = take(heads_tc_image_bytes(s.H, s.K, s.M, 1));
+        w.sv.t_b2 = take(heads_tc_image_bytes(s.H, s.K, s.M, 2));
+    }
     const FeDims fd{s.S, s.T, s.C, s.H};
     w.fe_bytes = (precision == FVAE_PREC_BF16_TC) ? fe_tc_workspace_bytes(fd) : fe_f32_workspace_bytes(fd);
     w.fe_ws = take(w.fe_bytes);
@@ -139,7 +148,7 @@ HeadsArgs make_heads_args(const fvae_shape& s, const Workspace& W, const float* 
     HeadsArgs a;
     a.S = s.S; a.B = s.B; a.H = s.H; a.K = s.K; a.M = s.M;
     a.date_ptr = date_ptr; a.e = W.e; a.y = y; a.noise = nz; a.flags = flags; a.predict = predict;
-    a.out = out; a.w = hw; a.sv = W.sv;
+    a.out = out; a.w = hw; a.sv = W.sv; a.use_tc = 0;
     return a;
 }
 
@@ -242,6 +251,7 @@ int fvae_elbo_backward(const fvae_shape* shape, const fvae_panel* x, const float
     bind_params(params, L, fw, hw);
     bind_grads(grad, L, fg, hg);
     HeadsArgs a = make_heads_args(*shape, W, y, date_ptr, *noise, flags, 0, *out, hw);
+    a.use_tc = (precision == FVAE_PREC_BF16_TC) ? 1 : 0;
     const FeDims fd{shape->S, shape->T, shape->C, shape->H};
     cudaError_t ce = cudaMemsetAsync(grad, 0, size_t(L.off[FVAE_P_NUM_SECTIONS]) * sizeof(float), st);
     if (ce != cudaSuccess) return int(ce);

@@ -52,23 +52,6 @@ __device__ __forceinline__ void load_row(float (&w)[HP], const float* __restrict
     for (int h = 0; h < HP; ++h) w[h] = (active && h < H) ? src[h] : 0.f;
 }
 
-__device__ __forceinline__ float keep_factor(const HeadsArgs& a, int unit, int k) {
-    // dropout on the attention scores (module.py:144): kept -> 1/0.9, dropped -> 0; eval -> 1
-    if (!(a.flags & FVAE_FLAG_TRAIN)) return 1.f;
-    bool keep;
-    if (a.noise.keep_mask) keep = a.noise.keep_mask[size_t(unit) * a.K + k] != 0;
-    else keep = philox_keep(a.noise.seed, a.noise.step, a.noise.unit_base + unit, k);
-    return keep ? kKeepScale : 0.f;
-}
-
-__device__ __forceinline__ float eps_of(const HeadsArgs& a, int unit) {
-    if (a.noise.eps) return a.noise.eps[unit];
-    return philox_normal(a.noise.seed, a.noise.step, a.noise.unit_base + unit);
-}
-
-// relu that propagates NaN like torch (fmaxf would swallow it)
-__device__ __forceinline__ float relu_nan(float s) { return (s > 0.f || s != s) ? s : 0.f; }
-
 struct Smem {
     float *Es, *ys, *aux0, *aux1, *red, *yp, *muz, *sgz, *mupr, *sgpr, *pooled, *ctx, *F;
     int* bad;
@@ -443,7 +426,8 @@ __device__ __forceinline__ ColRef col_ref(const HeadsArgs& a, int c) {
 }
 
 // WSM: the stacked weight rows [Wp; G; Wb; Wa] are staged in shared memory for the dE sweep
-template <int HP, int NB, bool WSM>
+// VEC: stop after the per-date vector phase and hand dyp / dp_k / pooled_k.dp_k to the tensor-core sweep (heads_tc.cu)
+template <int HP, int NB, bool WSM, bool VEC = false>
 __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, float* __restrict__ dE) {
     extern __shared__ __align__(16) float smem_raw[];
     const int H = a.H, K = a.K, M = a.M;
@@ -646,6 +630,12 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         pdp[k] = v;
     }
     __syncthreads();
+    if (VEC) {
+        for (int j = tid; j < M; j += NT) a.sv.t_dyp[size_t(d) * M + j] = dyp[j];
+        for (int idx = tid; idx < K * H; idx += NT) a.sv.t_dps[size_t(d) * K * H + idx] = dps[idx];
+        for (int k = tid; k < K; k += NT) a.sv.t_pdp[size_t(d) * K + k] = pdp[k];
+        return;
+    }
 
     // ---- pass C2: Z sweep -> weight gradients (registers) and dE
     // thread = (weight row c, stock slice): rows per batch cpb2, NS2 slices, NB batches of rows
@@ -875,6 +865,9 @@ size_t fwd_smem_bytes(int HP, int H, int K, int M) {
     if (mg > mx) mx = mg;
     return (f + mx) * sizeof(float);
 }
+size_t bwd_vec_smem_bytes(int HP, int H, int K, int M) {
+    return (size_t(CH) * HP + 5 * CH + 32 + 4 * size_t(M) + 10 * size_t(K) + 3 * size_t(K) * H) * sizeof(float);
+}
 size_t bwd_smem_bytes(int HP, int H, int K, int M, bool wsm) {
     size_t f = size_t(CH) * HP + 5 * CH + 32 + 4 * size_t(M) + 10 * size_t(K) + 3 * size_t(K) * H
              + size_t(CH) * (K | 1) + size_t(CH) * ((M + 2 * K + H) | 1);
@@ -925,6 +918,20 @@ int heads_forward(const HeadsArgs& a, cudaStream_t stream) {
 
 int heads_backward(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t stream) {
     const int HP = pick_hp(a.H);
+    if (a.use_tc && heads_tc_supported(a.H, a.K, a.M)) {
+        // vector phase per date on CUDA cores, then the stock sweep on tcgen05
+        const size_t vsm = bwd_vec_smem_bytes(HP, a.H, a.K, a.M);
+        int rcv;
+        if (HP == 20) {
+            if ((rcv = set_smem(heads_bwd_kernel<20, 1, false, true>, vsm)) != 0) return rcv;
+            heads_bwd_kernel<20, 1, false, true><<<a.B, NT, vsm, stream>>>(a, g, dE); count_launch();
+        } else {
+            if ((rcv = set_smem(heads_bwd_kernel<32, 1, false, true>, vsm)) != 0) return rcv;
+            heads_bwd_kernel<32, 1, false, true><<<a.B, NT, vsm, stream>>>(a, g, dE); count_launch();
+        }
+        if ((rcv = int(cudaGetLastError())) != 0) return rcv;
+        return heads_tc_sweep(a, g, dE, stream);
+    }
     const int NF = a.M + 2 * a.K + a.H;
     const int NB = (NF + NT - 1) / NT;
     if (NB > 3 || (NB == 3 && HP != 32)) return FVAE_ERR_LIMIT;

@@ -38,6 +38,12 @@ struct HeadsSaved {   // per-step state kept in the workspace between forward an
     float *pre_sg_post, *pre_sg_prior;  // [B][K]  softplus inputs
     int *bad;                         // [B][K]  NaN/Inf guard tripped (module.py:149)
     int *clamp_post, *clamp_prior;    // [B][K]  sigma == 0 -> 1e-6 fired (module.py:117 / :265)
+    // tensor-core backward sweep (heads_tc.cu): per-date vectors handed from the vector kernel to the sweep kernel
+    float *t_dyp;        // [B][M]     d loss / d y_p
+    float *t_dps;        // [B][K][H]  dp_k = Wv_k^T dctx_k
+    float *t_pdp;        // [B][K]     pooled_k . dp_k
+    float *t_dmuz;       // [B][K]     spare
+    void *t_b1, *t_b2;   // bf16 operand images of the stacked weight rows (date independent part)
 };
 
 struct HeadsArgs {
@@ -48,10 +54,48 @@ struct HeadsArgs {
     fvae_noise noise;
     uint32_t flags;
     int predict;                // 1: FactorVAE.prediction (prior factors into the decoder)
+    int use_tc;                 // FVAE_PREC_BF16_TC: the backward sweep may run on tcgen05 (heads_tc.cu)
     fvae_outputs out;
     HeadsW w;
     HeadsSaved sv;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float keep_factor(const HeadsArgs& a, int unit, int k) {
+    // dropout on the attention scores (module.py:144): kept -> 1/0.9, dropped -> 0; eval -> 1
+    if (!(a.flags & FVAE_FLAG_TRAIN)) return 1.f;
+    bool keep;
+    if (a.noise.keep_mask) keep = a.noise.keep_mask[size_t(unit) * a.K + k] != 0;
+    else keep = philox_keep(a.noise.seed, a.noise.step, a.noise.unit_base + unit, k);
+    return keep ? kKeepScale : 0.f;
+}
+__device__ __forceinline__ float eps_of(const HeadsArgs& a, int unit) {
+    if (a.noise.eps) return a.noise.eps[unit];
+    return philox_normal(a.noise.seed, a.noise.step, a.noise.unit_base + unit);
+}
+// relu that propagates NaN like torch (fmaxf would swallow it)
+__device__ __forceinline__ float relu_nan(float s) { return (s > 0.f || s != s) ? s : 0.f; }
+#endif
+
+// tensor-core backward sweep (heads_tc.cu): column layout of the stacked weight rows, padded to 8-column groups
+struct TcCols {
+    int Kp, Hp8;                 // K, H padded to 8
+    int c_att, c_beta, c_alpha, c_atta;   // group starts: [0,M) encoder | attention scores | beta | alpha | attention dp
+    int NZ;                      // total, padded to 16
+};
+__host__ __device__ inline TcCols tc_cols(int H, int K, int M) {
+    TcCols c;
+    c.Kp = (K + 7) & ~7; c.Hp8 = (H + 7) & ~7;
+    c.c_att = M; c.c_beta = M + c.Kp; c.c_alpha = M + 2 * c.Kp; c.c_atta = M + 2 * c.Kp + c.Hp8;
+    c.NZ = (M + 3 * c.Kp + c.Hp8 + 15) & ~15;
+    return c;
+}
+inline bool heads_tc_supported(int H, int K, int M) {
+    return (M % 8 == 0) && H <= 31 && tc_cols(H, K, M).NZ <= 256;
+}
+int64_t heads_tc_image_bytes(int H, int K, int M, int which);     // which: 1 = forward-product image, 2 = dE image
+int heads_tc_prep(const HeadsArgs& a, cudaStream_t stream);        // builds the images (after heads_prep)
+int heads_tc_sweep(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t stream);
 
 // all launchers are asynchronous on `stream` and return a cudaError_t as int
 int heads_prep(const HeadsArgs& a, bool zero_grad_acc, cudaStream_t stream);

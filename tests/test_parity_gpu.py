@@ -302,3 +302,49 @@ def test_bf16_tc_chain_vs_fp32_kernels(shape, cuda_device):
     assert not bad, (bad, report)
     assert _cos(g16, g32) >= 0.999
     assert float((g16.double() - g32.double()).norm() / g32.double().norm()) <= 3e-2
+
+
+@pytest.mark.parametrize("case", ["ragged", "many_dates", "one_date_many_tiles", "guard"])
+def test_bf16_tc_heads_sweep_sections_vs_fp32_kernels(case, cuda_device):
+    """The tcgen05 backward sweep of the heads (heads_tc.cu) against the fp32 CUDA-core chain, per parameter section:
+    ragged dates (tile tails, 1-stock dates), more dates than CTAs, one date spanning many tiles, a tripped guard."""
+    from factorvae_b200 import engine
+    import factorvae_b200 as fb
+    H, K, T = 20, 20, 3
+    torch.manual_seed(23)
+    m = fb.FactorVAE(fb.FeatureExtractor(158, H), fb.FactorEncoder(K, 128, H),
+                     fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, K)), fb.FactorPredictor(H, K))
+    sd = m.state_dict()
+    if case == "guard":
+        sd["factor_predictor.attention_layers.3.query"][0] = float("inf")
+    L = engine.ParamLayout(158, H, K, 128)
+    flat = L.pack(sd, cuda_device)
+    counts = {"ragged": [1, 128, 129, 300, 77, 256, 5], "many_dates": [9] * 400, "one_date_many_tiles": [2000],
+              "guard": [150, 90]}[case]
+    ptr = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=cuda_device)
+    S = int(ptr[-1])
+    g = torch.Generator(device=cuda_device).manual_seed(4)
+    x = torch.randn(S, T, 158, device=cuda_device, generator=g).clamp_(-3, 3)
+    y = torch.randn(S, device=cuda_device, generator=g)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        out, st = engine.elbo_forward(L, flat, x, y, ptr, train=True, precision=prec, philox=(5, 2, 0))
+        res[prec] = (out, engine.elbo_backward(L, st).clone())
+    (o32, g32), (o16, g16) = res["fp32"], res["bf16"]
+    assert torch.isfinite(g16).all()
+    names = list(L.offsets)                                   # C-ABI sections (attention layers stacked)
+    bounds = [L.offsets[n] for n in names] + [L.total]
+    sec = lambda gr, i: gr[bounds[i]:bounds[i + 1]].double()
+    gmax = max(float(sec(g32, i).norm()) for i in range(len(names)))
+    report = {}
+    for i, n in enumerate(names):
+        a, b = sec(g16, i), sec(g32, i)
+        if float(b.norm()) < 1e-3 * gmax:
+            assert float((a - b).norm()) <= 1e-3 * gmax, n
+            continue
+        report[n] = (float((a - b).norm() / b.norm()), _cos(a, b))
+    bad = {k: v for k, v in report.items() if not (v[0] <= 8e-2 and v[1] >= 0.997)}
+    assert not bad, (bad, report)
+    assert _cos(g16, g32) >= 0.999
+    if case == "guard":   # the tripped head gets exact zeros (module.py:149-150)
+        assert float(L.view(g16, "factor_predictor.attention_layers.3.query").abs().max()) == 0.0
