@@ -49,7 +49,7 @@ Workspace carve(const fvae_shape& s, int precision, void* base) {
     w.sv.t_dyp = reinterpret_cast<float*>(take(B * M * 4));
     w.sv.t_dps = reinterpret_cast<float*>(take(B * K * H * 4));
     w.sv.t_pdp = reinterpret_cast<float*>(take(B * K * 4));
-    w.sv.t_dmuz = nullptr;
+    w.sv.t_tile_ptr = reinterpret_cast<int*>(take((B + 1) * 4));
     w.sv.t_b1 = w.sv.t_b2 = nullptr;
     if (precision == FVAE_PREC_BF16_TC && heads_tc_supported(s.H, s.K, s.M)) {
         w.sv.t_b1 = take(heads_tc_image_bytes(s.H, s.K, s.M, 1));

@@ -42,7 +42,7 @@ struct HeadsSaved {   // per-step state kept in the workspace between forward an
     float *t_dyp;        // [B][M]     d loss / d y_p
     float *t_dps;        // [B][K][H]  dp_k = Wv_k^T dctx_k
     float *t_pdp;        // [B][K]     pooled_k . dp_k
-    float *t_dmuz;       // [B][K]     spare
+    int *t_tile_ptr;     // [B+1]      prefix of 128-stock tiles per date
     void *t_b1, *t_b2;   // bf16 operand images of the stacked weight rows (date independent part)
 };
 
@@ -80,19 +80,22 @@ __device__ __forceinline__ float relu_nan(float s) { return (s > 0.f || s != s) 
 // tensor-core backward sweep (heads_tc.cu): column layout of the stacked weight rows, padded to 8-column groups
 struct TcCols {
     int Kp, Hp8;                 // K, H padded to 8
-    int c_att, c_beta, c_alpha, c_atta;   // group starts: [0,M) encoder | attention scores | beta | alpha | attention dp
-    int NZ;                      // total, padded to 16
+    int c_att, c_beta, c_alpha;  // static groups: [0,M) encoder | attention scores | beta | alpha hidden
+    int NS;                      // static columns, padded to 16
+    int c_atta;                  // = NS: 32 per-date columns (attention weights; rows = dp_k of the date)
+    int NZ;                      // NS + 32
 };
 __host__ __device__ inline TcCols tc_cols(int H, int K, int M) {
     TcCols c;
     c.Kp = (K + 7) & ~7; c.Hp8 = (H + 7) & ~7;
-    c.c_att = M; c.c_beta = M + c.Kp; c.c_alpha = M + 2 * c.Kp; c.c_atta = M + 2 * c.Kp + c.Hp8;
-    c.NZ = (M + 3 * c.Kp + c.Hp8 + 15) & ~15;
+    c.c_att = M; c.c_beta = M + c.Kp; c.c_alpha = M + 2 * c.Kp;
+    c.NS = (M + 2 * c.Kp + c.Hp8 + 15) & ~15;
+    c.c_atta = c.NS;
+    c.NZ = c.NS + 32;
     return c;
 }
-inline bool heads_tc_supported(int H, int K, int M) {
-    return (M % 8 == 0) && H <= 31 && tc_cols(H, K, M).NZ <= 256;
-}
+// M == 128: the encoder rows fill exactly the first 128-column block (one UMMA M block of the weight-gradient GEMM)
+inline bool heads_tc_supported(int H, int K, int M) { return M == 128 && H <= 31 && K <= 32; }
 int64_t heads_tc_image_bytes(int H, int K, int M, int which);     // which: 1 = forward-product image, 2 = dE image
 int heads_tc_prep(const HeadsArgs& a, cudaStream_t stream);        // builds the images (after heads_prep)
 int heads_tc_sweep(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t stream);
