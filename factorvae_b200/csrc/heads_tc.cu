@@ -26,10 +26,19 @@ namespace {
 
 using namespace tc;
 
-constexpr int TNT = 512;                       // 4 column parts x 128 rows
+constexpr int TNT = 512;                       // transform threads: 4 column parts x 128 rows
+constexpr int TNT_ALL = TNT + 32;              // + one warp that only issues the UMMAs
 constexpr float kL2E = 1.4426950408889634f;
 constexpr int kHK = 32;                        // K extent of the E tile: H columns + ones column, padded
 
+__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float sanitize(float v) { return fabsf(v) <= FLT_MAX ? v : 0.f; }
 
 struct RowRef { const float* w; float bias; int kind; int idx; };   // kind: 0 enc, 1 att, 2 beta, 3 alpha, -1 none
@@ -99,7 +108,7 @@ __host__ __device__ inline SweepSmem sweep_layout(int M, const TcCols& tcg) {
     s.bet2 = take(2u * 32u * 8u);
     s.alw = take((2u * 32u + 1u) * 4u);
     s.accal = take(64u * 4u);
-    s.bar = take(16);
+    s.bar = take(32);
     s.slot = take(16);
     s.start = take(16);
     s.total = p;
@@ -142,7 +151,7 @@ constexpr uint32_t kColDE = 256, kColDW = 320;
 
 struct TileIt { int d, t, p0, n; };   // date, tile inside the date, first unit of the date, stocks of the date
 
-__global__ void __launch_bounds__(TNT, 1) heads_tc_sweep_kernel(HeadsArgs a, HeadsG g, float* __restrict__ dE, TcCols tcg) {
+__global__ void __launch_bounds__(TNT_ALL, 1) heads_tc_sweep_kernel(HeadsArgs a, HeadsG g, float* __restrict__ dE, TcCols tcg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int H = a.H, K = a.K, M = a.M, NS = tcg.NS;
     const int tid = threadIdx.x, row = tid & 127, part = tid >> 7, warp = tid >> 5, lane = tid & 31;
@@ -159,33 +168,36 @@ __global__ void __launch_bounds__(TNT, 1) heads_tc_sweep_kernel(HeadsArgs a, Hea
     float* alw = reinterpret_cast<float*>(smem + L.alw);       // wam[32] | was[32] | bas
     float* accal = reinterpret_cast<float*>(smem + L.accal);   // [0,32): d wam (31: d bam) | [32,64): d was (63: d bas)
     uint64_t* barA = reinterpret_cast<uint64_t*>(smem + L.bar);
-    uint64_t* barB = barA + 1;
+    uint64_t* barB = barA + 1;                                 // MMA groups complete -> transform threads
+    uint64_t* zA = barA + 2;                                   // encoder half of Z (and the next E tile) written -> issuer
+    uint64_t* zB = barA + 3;
+    const bool issuer = warp == TNT / 32;
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem + L.slot);
     int* s_start = reinterpret_cast<int*>(smem + L.start);
 
     if (warp == 0) tmem_alloc<512>(slot);
-    if (tid == 0) { mbar_init(barA, 1); mbar_init(barB, 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(barA, 1); mbar_init(barB, 1); mbar_init(zA, TNT); mbar_init(zB, TNT); mbar_fence_init(); }
     // my contiguous range of 128-stock tiles
     const int total = a.sv.t_tile_ptr[a.B];
     const int per = (total + int(gridDim.x) - 1) / int(gridDim.x);
     const int lo = int(blockIdx.x) * per, hi = min(total, lo + per);
     if (lo < hi)
-        for (int d = tid; d < a.B; d += TNT) {
+        for (int d = tid; d < a.B; d += TNT_ALL) {
             const int t0 = a.sv.t_tile_ptr[d], t1 = a.sv.t_tile_ptr[d + 1];
             if (t0 <= lo && lo < t1) { s_start[0] = d; s_start[1] = lo - t0; }
         }
     {   // static images, zeroed Z tile, alpha-layer vectors
         const uint4* s1 = static_cast<const uint4*>(a.sv.t_b1);
-        for (int i = tid; i < 8 * NS; i += TNT) reinterpret_cast<uint4*>(B1s)[i] = s1[i];
+        for (int i = tid; i < 8 * NS; i += TNT_ALL) reinterpret_cast<uint4*>(B1s)[i] = s1[i];
         const uint4* s2 = static_cast<const uint4*>(a.sv.t_b2);
-        for (int i = tid; i < NS * 4; i += TNT) reinterpret_cast<uint4*>(B2s)[i] = s2[i];
-        for (int i = tid; i < 32 * 128; i += TNT) reinterpret_cast<uint4*>(Zt)[i] = make_uint4(0, 0, 0, 0);
-        for (int j = tid; j < 32; j += TNT) {
+        for (int i = tid; i < NS * 4; i += TNT_ALL) reinterpret_cast<uint4*>(B2s)[i] = s2[i];
+        for (int i = tid; i < 32 * 128; i += TNT_ALL) reinterpret_cast<uint4*>(Zt)[i] = make_uint4(0, 0, 0, 0);
+        for (int j = tid; j < 32; j += TNT_ALL) {
             alw[j] = (j < H) ? a.w.wam[j] : 0.f;
             alw[32 + j] = (j < H) ? a.w.was[j] : 0.f;
         }
         if (tid == 0) alw[64] = a.w.bas[0];
-        for (int j = tid; j < 64; j += TNT) accal[j] = 0.f;
+        for (int j = tid; j < 64; j += TNT_ALL) accal[j] = 0.f;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -274,18 +286,50 @@ __global__ void __launch_bounds__(TNT, 1) heads_tc_sweep_kernel(HeadsArgs a, Hea
     if (ntiles > 0) {
         TileIt cur; cur.d = s_start[0]; cur.t = s_start[1]; load_date(cur);
         int pb = 0;                                          // date parity buffer of `cur`
-        stage_date(cur.d, pb);
-        { float v[8]; load_e(cur, v); store_e(0, v); }
+        if (!issuer) {
+            stage_date(cur.d, pb);
+            float v[8]; load_e(cur, v); store_e(0, v);
+        }
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            issue_f(0, b1s_addr, NS, 0, 128, 0);
-            mma_commit(barA);
-            issue_f(0, b1s_addr, NS, 128, uint32_t(NS - 128), 128);
-            issue_f(0, b1d_addr + pb * kB1dBytes, 32, 0, 32, uint32_t(NS));
-            mma_commit(barB);
-        }
+        if (issuer) {
+            // ---- UMMA issuer warp: waits for the halves of Z, issues dE / dW of this tile and F of the next one
+            if (lane == 0) {
+                tc_fence_after_sync();
+                issue_f(0, b1s_addr, NS, 0, 128, 0);
+                mma_commit(barA);
+                issue_f(0, b1s_addr, NS, 128, uint32_t(NS - 128), 128);
+                issue_f(0, b1d_addr + pb * kB1dBytes, 32, 0, 32, uint32_t(NS));
+                mma_commit(barB);
+                uint32_t pzA = 0, pzB = 0;
+                for (int g_i = 0; g_i < ntiles; ++g_i) {
+                    const bool has_next = g_i + 1 < ntiles;
+                    TileIt nxt = cur;
+                    if (has_next) advance(nxt);
+                    const int pbn = (has_next && nxt.d != cur.d) ? (pb ^ 1) : pb;
+                    const uint32_t e_cur = et_addr + (g_i % 3) * 8 * kTileChunk;
+                    const uint32_t decol = kColDE + 32u * (g_i & 1);
+                    mbar_wait(zA, pzA); pzA ^= 1;
+                    tc_fence_after_sync();
+                    issue_row_gemm_acc(tmem, decol, zt_addr, b2s_addr, kHK, kHK, 8, false);              // dE: encoder part
+                    issue_wgrad_acc(tmem, kColDW, zt_addr, 0, e_cur, kHK, g_i > 0);
+                    if (has_next) issue_f((g_i + 1) % 3, b1s_addr, NS, 0, 128, 0);
+                    mma_commit(barA);
+                    mbar_wait(zB, pzB); pzB ^= 1;
+                    tc_fence_after_sync();
+                    issue_row_gemm_acc(tmem, decol, zt_addr + 16 * kTileChunk, b2s_addr + 16 * (kHK * 16), kHK, kHK, (NS - 128) / 16, true);
+                    issue_row_gemm_acc(tmem, decol, zt_addr + uint32_t(NS / 8) * kTileChunk, b2d_addr + pb * kB2dBytes, kHK, kHK, 2, true);
+                    issue_wgrad_acc(tmem, kColDW + 32u, zt_addr, 16, e_cur, kHK, g_i > 0);
+                    if (has_next) {
+                        issue_f((g_i + 1) % 3, b1s_addr, NS, 128, uint32_t(NS - 128), 128);
+                        issue_f((g_i + 1) % 3, b1d_addr + pbn * kB1dBytes, 32, 0, 32, uint32_t(NS));
+                    }
+                    mma_commit(barB);
+                    cur = nxt; pb = pbn;
+                }
+            }
+            __syncwarp();
+        } else {
         TileIt prev = cur;
         for (int g_i = 0; g_i < ntiles; ++g_i) {
             const bool has_next = g_i + 1 < ntiles;
@@ -312,7 +356,7 @@ __global__ void __launch_bounds__(TNT, 1) heads_tc_sweep_kernel(HeadsArgs a, Hea
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 e4 = e4v[ch * 8 + q];
-                        z[q] = valid ? exp2f(fmaf(f[q], kL2E, e4.x)) * e4.y * (yi - e4.z) : 0.f;
+                        z[q] = valid ? ex2_fast(fmaf(f[q], kL2E, e4.x)) * e4.y * (yi - e4.z) : 0.f;
                     }
                     store8(Zt + tile_off(128, row, ch), z);
                 }
@@ -320,19 +364,15 @@ __global__ void __launch_bounds__(TNT, 1) heads_tc_sweep_kernel(HeadsArgs a, Hea
             if (has_next) store_e((g_i + 1) % 3, en);
             fence_async_smem();
             tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                issue_row_gemm_acc(tmem, kColDE + 32u * (g_i & 1), zt_addr, b2s_addr, kHK, kHK, 8, false);   // dE: encoder part
-                issue_wgrad_acc(tmem, kColDW, zt_addr, 0, et_addr + (g_i % 3) * 8 * kTileChunk, kHK, g_i > 0);
-                if (has_next) issue_f((g_i + 1) % 3, b1s_addr, NS, 0, 128, 0);
-                mma_commit(barA);
-            }
+            mbar_arrive(zA);
             // ---- phase B: attention, beta, alpha columns
             mbar_wait(barB, phB); phB ^= 1;
             tc_fence_after_sync();
             if (g_i > 0) store_de(prev, (g_i - 1) & 1);
-            if (new_date) stage_date(nxt.d, pbn);
+            if (new_date) {                                   // next date's vectors: visible to every transform thread before its phase A
+                stage_date(nxt.d, pbn);
+                asm volatile("bar.sync 1, %0;" ::"n"(TNT) : "memory");
+            }
             if (part < 3) {                                   // attention: d score and the weights a_ik
                 const float4* a4v = att4 + pb * 32;
                 for (int kc = part; kc < tcg.Kp / 8; kc += 3) {
@@ -412,24 +452,15 @@ __global__ void __launch_bounds__(TNT, 1) heads_tc_sweep_kernel(HeadsArgs a, Hea
             }
             fence_async_smem();
             tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                const uint32_t decol = kColDE + 32u * (g_i & 1);
-                issue_row_gemm_acc(tmem, decol, zt_addr + 16 * kTileChunk, b2s_addr + 16 * (kHK * 16), kHK, kHK, (NS - 128) / 16, true);
-                issue_row_gemm_acc(tmem, decol, zt_addr + uint32_t(NS / 8) * kTileChunk, b2d_addr + pb * kB2dBytes, kHK, kHK, 2, true);
-                issue_wgrad_acc(tmem, kColDW + 32u, zt_addr, 16, et_addr + (g_i % 3) * 8 * kTileChunk, kHK, g_i > 0);
-                if (has_next) {
-                    issue_f((g_i + 1) % 3, b1s_addr, NS, 128, uint32_t(NS - 128), 128);
-                    issue_f((g_i + 1) % 3, b1d_addr + pbn * kB1dBytes, 32, 0, 32, uint32_t(NS));
-                }
-                mma_commit(barB);
-            }
+            mbar_arrive(zB);
             prev = cur; cur = nxt; pb = pbn;
         }
         mbar_wait(barB, phB); phB ^= 1;
         tc_fence_after_sync();
         store_de(prev, (ntiles - 1) & 1);
+        }
+        __syncthreads();
+        if (!issuer) {
         // all MMAs of the encoder block were committed to barA before the last barB commit: complete as well
         // ---- flush the weight-gradient accumulators: TMEM lane = stacked row c, column = h (bias at h = H)
         if (part < 2) {
@@ -452,16 +483,23 @@ __global__ void __launch_bounds__(TNT, 1) heads_tc_sweep_kernel(HeadsArgs a, Hea
             else if (r.kind == 2) { gw = g.Wb + size_t(r.idx) * H; gb = g.bb + r.idx; }
             else if (r.kind == 3) { gw = g.Wa + size_t(r.idx) * H; gb = g.ba + r.idx; }
             if (gw) {
+                if ((H & 3) == 0) {                           // rows are 16-byte aligned: one vector reduction per 4 columns
 #pragma unroll
-                for (int h = 0; h < 32; ++h) {
-                    if (h < H) atomicAdd(gw + h, w[h]);
-                    else if (h == H) atomicAdd(gb, w[h]);
+                    for (int h4 = 0; h4 < 8; ++h4)
+                        if (4 * h4 < H) red_add_v4(gw + 4 * h4, w[4 * h4], w[4 * h4 + 1], w[4 * h4 + 2], w[4 * h4 + 3]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 32; ++h) if (h < H) atomicAdd(gw + h, w[h]);
                 }
+#pragma unroll
+                for (int h = 0; h < 32; ++h) if (h == H) atomicAdd(gb, w[h]);
             }
+        } else if (part == 3) {
+            const int j = tid - 3 * 128;
+            if (j < H) { atomicAdd(g.wam + j, accal[j]); atomicAdd(g.was + j, accal[32 + j]); }
+            if (j == 31) { atomicAdd(g.bam, accal[31]); atomicAdd(g.bas, accal[63]); }
         }
-        __syncthreads();
-        for (int j = tid; j < H; j += TNT) { atomicAdd(g.wam + j, accal[j]); atomicAdd(g.was + j, accal[32 + j]); }
-        if (tid == 0) { atomicAdd(g.bam, accal[31]); atomicAdd(g.bas, accal[63]); }
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -491,7 +529,7 @@ int heads_tc_sweep(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t 
     if (e != cudaSuccess) return int(e);
     int rc = heads_tc_prep(a, stream);
     if (rc != 0) return rc;
-    heads_tc_sweep_kernel<<<sms, TNT, L.total, stream>>>(a, g, dE, c); count_launch();
+    heads_tc_sweep_kernel<<<sms, TNT_ALL, L.total, stream>>>(a, g, dE, c); count_launch();
     return int(cudaGetLastError());
 }
 
