@@ -46,6 +46,8 @@ Workspace carve(const fvae_shape& s, int precision, void* base) {
     w.sv.bad = reinterpret_cast<int*>(take(B * K * 4));
     w.sv.clamp_post = reinterpret_cast<int*>(take(B * K * 4));
     w.sv.clamp_prior = reinterpret_cast<int*>(take(B * K * 4));
+    w.sv.c1_mu = reinterpret_cast<float*>(take(B * K * 4));
+    w.sv.c1_sg = reinterpret_cast<float*>(take(B * K * 4));
     w.sv.t_dyp = reinterpret_cast<float*>(take(B * M * 4));
     w.sv.t_dps = reinterpret_cast<float*>(take(B * K * H * 4));
     w.sv.t_pdp = reinterpret_cast<float*>(take(B * K * 4));

@@ -339,6 +339,8 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
 
     // ---- pass B: decoder per stock (module.py:109-123) + squared error of the sample
     float rec_part = 0.f;
+    float c1a = 0.f, c1b = 0.f;                                    // sum_i beta_ik dmu_y_i, sum_i beta_ik^2 dvar_i (for backward)
+    const float coefN = 2.f / (float(n) * float(a.B));
     const int ncolB = K + H;
     const int cpbB = ncolB < NT ? ncolB : NT;
     const int NSB = NT / cpbB;
@@ -395,10 +397,31 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
                 a.out.yhat[u] = yh; a.out.mu_y[u] = mu; a.out.sigma_y[u] = sy;
                 const float dlt = yh - s.ys[i];
                 rec_part = fmaf(dlt, dlt, rec_part);
+                const float dmy = coefN * dlt;                     // d loss / d mu_y ; d loss / d sigma_y^2 = dmy eps / (2 sigma_y)
+                s.aux1[i] = dmy;
+                s.ys[i] = dmy * s.aux0[i] / (2.f * sy);
+            } else if (i < CH && part == 0) {
+                s.aux1[i] = 0.f; s.ys[i] = 0.f;
             }
+        }
+        if (!a.predict) {
+            __syncthreads();
+            const int k = tid % K, slice = tid / K, NSC = NT / K;
+            if (slice < NSC)
+                for (int i = slice; i < cn; i += NSC) {
+                    const float b = s.F[i * FLD + k];
+                    c1a = fmaf(b, s.aux1[i], c1a);
+                    c1b = fmaf(b * b, s.ys[i], c1b);
+                }
         }
     }
     if (a.predict) return;
+    __syncthreads();
+    if (tid < 2 * K) s.F[tid] = 0.f;
+    __syncthreads();
+    if (tid / K < NT / K) { atomicAdd(&s.F[tid % K], c1a); atomicAdd(&s.F[K + tid % K], c1b); }
+    __syncthreads();
+    if (tid < K) { a.sv.c1_mu[size_t(d) * K + tid] = s.F[tid]; a.sv.c1_sg[size_t(d) * K + tid] = s.F[K + tid]; }
     const float rec = block_sum(rec_part, s.red) / float(n);           // F.mse_loss: mean over stocks
     float klp = 0.f;
     for (int k = tid; k < K; k += NT) {                                 // module.py:247
@@ -501,40 +524,10 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
     }
     __syncthreads();
 
-    // ---- pass C1: d mu_z[k] = sum_i beta_ik dmu_y_i ; d sigma_z[k] = 2 sigma_z[k] sum_i beta_ik^2 dv_i
-    {
-        const int cpb = K < NT ? K : NT;
-        const int NS1 = NT / cpb;
-        for (int kb = 0; kb < K; kb += cpb) {
-            const int k = kb + tid % cpb, slice = tid / cpb;
-            const bool act = k < K && slice < NS1;
-            float w[HP];
-            load_row<HP>(w, a.w.Wb + size_t(act ? k : 0) * H, H, act);
-            const float bias = act ? a.w.bb[k] : 0.f;
-            float acc1 = 0.f, acc2 = 0.f;
-            for (int i0 = 0; i0 < n; i0 += CH) {
-                const int cn = min(CH, n - i0);
-                __syncthreads();
-                stage_chunk<HP>(a, Smem{Es}, p0, i0, cn);
-                if (tid < CH) {
-                    float v1 = 0.f, v2 = 0.f;
-                    if (tid < cn) {
-                        const int u = p0 + i0 + tid;
-                        v1 = coefN * (a.out.yhat[u] - a.y[u]);
-                        v2 = v1 * eps_of(a, u) / (2.f * a.out.sigma_y[u]);
-                    }
-                    dmy[tid] = v1; dvv[tid] = v2;
-                }
-                __syncthreads();
-                if (act)
-                    for (int i = slice; i < cn; i += NS1) {
-                        const float b = dot_row<HP>(w, Es + i * HP) + bias;
-                        acc1 = fmaf(b, dmy[i], acc1);
-                        acc2 = fmaf(b * b, dvv[i], acc2);
-                    }
-            }
-            if (act) { atomicAdd(&dmupost[k], acc1); atomicAdd(&dprepost[k], 2.f * sgz[k] * acc2); }   // staged: d mu_z, d sigma_z
-        }
+    // ---- d mu_z[k] = sum_i beta_ik dmu_y_i ; d sigma_z[k] = 2 sigma_z[k] sum_i beta_ik^2 dvar_i  (sums saved by forward pass B)
+    for (int k = tid; k < K; k += NT) {
+        dmupost[k] = a.sv.c1_mu[size_t(d) * K + k];
+        dprepost[k] = 2.f * sgz[k] * a.sv.c1_sg[size_t(d) * K + k];
     }
     __syncthreads();
 

@@ -38,6 +38,7 @@ struct HeadsSaved {   // per-step state kept in the workspace between forward an
     float *pre_sg_post, *pre_sg_prior;  // [B][K]  softplus inputs
     int *bad;                         // [B][K]  NaN/Inf guard tripped (module.py:149)
     int *clamp_post, *clamp_prior;    // [B][K]  sigma == 0 -> 1e-6 fired (module.py:117 / :265)
+    float *c1_mu, *c1_sg;             // [B][K]  sum_i beta_ik dmu_y_i, sum_i beta_ik^2 dvar_i
     // tensor-core backward sweep (heads_tc.cu): per-date vectors handed from the vector kernel to the sweep kernel
     float *t_dyp;        // [B][M]     d loss / d y_p
     float *t_dps;        // [B][K][H]  dp_k = Wv_k^T dctx_k
