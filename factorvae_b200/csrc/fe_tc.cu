@@ -160,6 +160,7 @@ struct GruArgs {
     float* e;             // [S][H]
     const float* dE;      // [S][H]   (backward)
     float *gWhh, *gbhh;   // gradient sections (backward)
+    int gi_ring;          // forward: stream the gate pre-activation tiles through a 2-stage bulk-copy ring in shared memory
 };
 
 template <int NB8, uint32_t TCOLS>
@@ -171,11 +172,24 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
     unsigned char* sH = sWhh + uint32_t(HCH) * NC * 16;           // [HCH][128][16]
     float* sBhn = reinterpret_cast<float*>(sH + uint32_t(HCH) * TILE_CH);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sBhn + HP);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint64_t* full = bar + 1;                                     // [2] ring stages filled (bulk copy complete_tx)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+    unsigned char* sGi = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~uintptr_t(127));
+    const uint32_t gi_bytes = uint32_t(NCH) * TILE_CH;            // one step's tile [NCH][128][16]
+    const bool ring = a.gi_ring != 0;
     copy_image(sWhh, a.ws.whh, uint32_t(HCH) * NC * 16);
     for (int i = tid; i < HP; i += TM) sBhn[i] = a.ws.bhn[i];
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
+    // flattened (tile, step) sequence of this CTA: q -> tile blockIdx.x + (q / T) * gridDim.x, step q % T
+    const int64_t my_tiles = a.NT > int64_t(blockIdx.x) ? (a.NT - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t total_q = my_tiles * a.T;
+    auto fill = [&](int64_t q) {                                  // one thread: bulk copy of step q's tile into stage q & 1
+        const int64_t tile = int64_t(blockIdx.x) + (q / a.T) * gridDim.x;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(tile * a.T + q % a.T) * gi_bytes;
+        mbar_expect_tx(&full[q & 1], gi_bytes);
+        bulk_g2s(sGi + (q & 1) * gi_bytes, src, gi_bytes, &full[q & 1]);
+    };
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -183,12 +197,14 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = uint32_t(warp) * 32u;
     uint32_t phase = 0;
+    if (ring && tid == 0) { if (total_q > 0) fill(0); if (total_q > 1) fill(1); }
+    int64_t q = 0;
     for (int64_t st = blockIdx.x; st < a.NT; st += gridDim.x) {
         float h[8 * NB8];
 #pragma unroll
         for (int j = 0; j < 8 * NB8; ++j) h[j] = 0.f;
         const int64_t s = st * TM + tid;
-        for (int t = 0; t < a.T; ++t) {
+        for (int t = 0; t < a.T; ++t, ++q) {
             if (t > 0) {
                 fence_async_smem();
                 tc_fence_before_sync();
@@ -199,11 +215,21 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
                     mma_commit(bar);
                 }
             }
-            // my row's gate pre-activations of this step: in flight while the MMA runs
-            const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
+            // a CTA barrier (this step's, or the one that closed the previous tile) separates everybody's reads of
+            // step q-1's stage from its refill with step q+1
+            if (ring && tid == 0 && q >= 1 && q + 1 < total_q) fill(q + 1);
+            // my row's gate pre-activations of this step
             uint4 gq[3 * NB8];
+            if (ring) {
+                mbar_wait(&full[q & 1], uint32_t(q >> 1) & 1u);
+                const unsigned char* gin = sGi + (q & 1) * gi_bytes;
 #pragma unroll
-            for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, c));
+                for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, c));
+            } else {                                              // direct global loads, in flight while the MMA runs
+                const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
+#pragma unroll
+                for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, c));
+            }
             if (t > 0) {
                 mbar_wait(bar, phase);
                 phase ^= 1;
@@ -298,6 +324,14 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
         const int64_t s = st * TM + tid;
 #pragma unroll
         for (int j = 0; j < 8 * NB8; ++j) dh[j] = (s < a.S && j < H) ? a.dE[s * H + j] : 0.f;
+        // my row's gate pre-activations: step T-1 here, step t-1 right after step t's gate epilogue (its registers are
+        // free by then), so the load latency hides behind the dh GEMM and the next step's gh GEMM
+        uint4 gq[3 * NB8];
+        {
+            const unsigned char* g0 = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + a.T - 1) * NCH * TILE_CH;
+#pragma unroll
+            for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(g0 + tile_off(TM, tid, c));
+        }
         for (int t = a.T - 1; t >= 0; --t) {
             if (dw_pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; dw_pending = false; }   // sHp / sDgh are free again
             // h_{t-1} operand tile (my row of it was prefetched into registers during the previous step)
@@ -328,11 +362,8 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
                 issue_row_gemm(tmem, 0, smem_u32(sHp), smem_u32(sWhh), NC, NC, HP / 16);
                 mma_commit(&bars[0]);
             }
-            // global loads in flight while the MMA runs: this step's gate pre-activations, next step's h_{t-2}
+            // global loads in flight while the MMA runs: next step's h_{t-2}
             unsigned char* gio = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
-            uint4 gq[3 * NB8];
-#pragma unroll
-            for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gio + tile_off(TM, tid, c));
             if (t > 1) {
                 const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 2) * HCH * TILE_CH;
 #pragma unroll
@@ -387,6 +418,11 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
                 *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b + 1)) = pz;
                 *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b + 2)) = pq;
             }
+            if (t > 0) {
+                const unsigned char* gn = gio - size_t(NCH) * TILE_CH;          // step t-1 of this tile
+#pragma unroll
+                for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gn + tile_off(TM, tid, c));
+            }
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -425,11 +461,22 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
                 float v[8];
                 tmem_ld8(tmem_addr(tmem, lane_base, COL_DW + mb * HP + c8 * 8), v);
                 if (ok) {
+                    float* grow = a.gWhh + size_t(gate * H + j) * H;
+                    if ((H & 3) == 0) {                           // 16-byte aligned rows: vector reductions
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int k = c8 * 8 + u;
-                        if (k < H) atomicAdd(a.gWhh + size_t(gate * H + j) * H + k, v[u]);
-                        else if (k == H) atomicAdd(a.gbhh + gate * H + j, v[u]);
+                        for (int u4 = 0; u4 < 2; ++u4) {
+                            const int k = c8 * 8 + 4 * u4;
+                            if (k < H) red_add_v4(grow + k, v[4 * u4], v[4 * u4 + 1], v[4 * u4 + 2], v[4 * u4 + 3]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (c8 * 8 + u == H) atomicAdd(a.gbhh + gate * H + j, v[u]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int k = c8 * 8 + u;
+                            if (k < H) atomicAdd(grow + k, v[u]);
+                            else if (k == H) atomicAdd(a.gbhh + gate * H + j, v[u]);
+                        }
                     }
                 }
             }
@@ -561,8 +608,12 @@ int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, 
     const int nsm = num_sms();
     int rc;
     if ((rc = fe_tc_front_only(d, x, wsp, st)) != 0) return rc;
-    GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, e, nullptr, nullptr, nullptr};
-    const size_t smem = size_t(HP / 8) * NC * 16 + size_t(HP / 8) * TILE_CH + HP * 4 + 64;
+    GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, e, nullptr, nullptr, nullptr, 0};
+    size_t smem = size_t(HP / 8) * NC * 16 + size_t(HP / 8) * TILE_CH + HP * 4 + 64;
+    {   // gate pre-activation ring: only while four CTAs still fit one SM
+        const size_t with_ring = smem + 256 + 2 * size_t(NC / 8) * TILE_CH;
+        if (NC <= 128 && with_ring <= 56 * 1024) { g.gi_ring = 1; smem = with_ring; }
+    }
     const int ctas_per_sm = NC <= 128 ? 4 : 2;
     const int grid = int(a.NT < int64_t(nsm) * ctas_per_sm ? a.NT : int64_t(nsm) * ctas_per_sm);
     if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 128>, grid, smem, st, g)); }
@@ -577,7 +628,7 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     const int nsm = num_sms();
     int rc;
     {   // BPTT
-        GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, nullptr, dE, gr.Whh, gr.bhh};
+        GruArgs g{d.S, d.T, d.H, NC, HP, a.NT, ws, nullptr, dE, gr.Whh, gr.bhh, 0};
         const int MB = NC > 128 ? 2 : 1;
         const size_t smem = size_t(HP / 8) * NC * 16 + size_t(NC / 8) * HP * 16 + size_t(HP / 8) * TILE_CH + size_t(16 * MB) * TILE_CH + HP * 4 + 64;
         const uint32_t cols = uint32_t(NC + MB * HP);

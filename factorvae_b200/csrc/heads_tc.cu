@@ -31,9 +31,6 @@ constexpr int TNT_ALL = TNT + 32;              // + one warp that only issues th
 constexpr float kL2E = 1.4426950408889634f;
 constexpr int kHK = 32;                        // K extent of the E tile: H columns + ones column, padded
 
-__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
 __device__ __forceinline__ float ex2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
