@@ -688,3 +688,126 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_from_tiles_kernel(ItemArgs a) {
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
+// ---- K4a (streaming variant): same math as tc_q_from_tiles_kernel, buffers decoupled so nothing waits on HBM -----
+// Shared memory: 2 xhat stages | 3 dGI stages | 1 dpre tile | W_ih^T image.  One thread feeds the stages with 1-D bulk
+// copies (complete_tx on mbarriers): dGI three items ahead (it gates du), xhat as soon as the Q MMAs of the item that
+// used the stage have completed (it is only needed by Q, one and a half iterations later).  du(k+1) is issued in front
+// of Q(k), so the dpre epilogue of item k+1 overlaps the Q MMAs of item k.  Used when the buffers fit (NC <= 96).
+__global__ void __launch_bounds__(NTH, 1) tc_q_stream_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
+    const int NC = a.NC, NCH = NC / 8;
+    const uint32_t g_bytes = uint32_t(NCH) * TILE_CH;
+    unsigned char* sX = smem;                                   // [2][A_BYTES]; the M-block over-read of stage 1 runs into sG
+    unsigned char* sG = sX + 2 * A_BYTES;                       // [3][g_bytes]
+    unsigned char* sD = sG + 3 * g_bytes;                       // dpre tile
+    unsigned char* sWihT = sD + A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sWihT + uint32_t(NCH) * CP * 16);
+    uint64_t* full_x = bars;            // [2]
+    uint64_t* full_g = bars + 2;        // [3]
+    uint64_t* bar_du = bars + 5;
+    uint64_t* bar_q = bars + 6;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
+    for (uint32_t i = tid; i < (2 * A_BYTES + 3 * g_bytes + A_BYTES) / 16; i += NTH) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+    constexpr uint32_t COL_DU = 0, COL_QA = 160, COL_QB0 = 320, COL_QB1 = 352;
+    const int64_t nitems = a.NT * a.T, G = gridDim.x;
+    const int64_t mine = nitems > int64_t(blockIdx.x) ? (nitems - 1 - blockIdx.x) / G + 1 : 0;   // my items: blockIdx.x + k G
+    auto load_x = [&](int64_t k) {      // one thread
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.ws.xh) + size_t(blockIdx.x + k * G) * A_BYTES;
+        mbar_expect_tx(&full_x[k & 1], A_BYTES);
+        bulk_g2s(sX + (k & 1) * A_BYTES, src, A_BYTES, &full_x[k & 1]);
+    };
+    auto load_g = [&](int64_t k) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(blockIdx.x + k * G) * g_bytes;
+        mbar_expect_tx(&full_g[k % 3], g_bytes);
+        bulk_g2s(sG + (k % 3) * g_bytes, src, g_bytes, &full_g[k % 3]);
+    };
+    auto issue_du = [&](int64_t k) {    // one thread; waits for the dGI tile of item k
+        mbar_wait(&full_g[k % 3], uint32_t(k / 3) & 1u);
+        issue_row_gemm(tmem, COL_DU, smem_u32(sG + (k % 3) * g_bytes), smem_u32(sWihT), CP, CP, NC / 16);
+        mma_commit(bar_du);
+    };
+    if (mine > 0) {
+        if (tid == 0) {
+            load_g(0); if (mine > 1) load_g(1); if (mine > 2) load_g(2);
+            load_x(0); if (mine > 1) load_x(1);
+            tc_fence_after_sync();
+            issue_du(0);
+        }
+        unsigned long long mbits = a.ws.mask[size_t(blockIdx.x) * 4 * TM + half * TM + row];
+        for (int64_t k = 0; k < mine; ++k) {
+            const bool has_next = k + 1 < mine;
+            unsigned long long mnext = 0ull;
+            if (has_next) mnext = a.ws.mask[size_t(blockIdx.x + (k + 1) * G) * 4 * TM + half * TM + row];
+            mbar_wait(bar_du, uint32_t(k) & 1u);               // du(k) is in TMEM; the dGI stage of item k is free
+            tc_fence_after_sync();
+            if (tid == 0 && k + 3 < mine) load_g(k + 3);
+            uint4 pk[HALF_CH];
+#pragma unroll
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                float d[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_DU + HALF_COLS * half + ch * 8), d);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[e] *= ((mbits >> (ch * 8 + e)) & 1ull) ? 1.f : kLeakySlope;
+                pk[ch] = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+            }
+            if (k > 0) {                                       // Q(k-1) done: the dpre tile and xhat stage (k-1)&1 are free
+                mbar_wait(&bar_q[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u);
+                if (tid == 0 && has_next) load_x(k + 1);
+            }
+#pragma unroll
+            for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sD + tile_off(TM, row, HALF_CH * half + ch)) = pk[ch];
+            fence_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                if (has_next) issue_du(k + 1);                 // in front of Q(k): COL_DU was read before the barrier
+                mbar_wait(&full_x[k & 1], uint32_t(k >> 1) & 1u);
+                const uint32_t xs = smem_u32(sX + (k & 1) * A_BYTES), ds = smem_u32(sD);
+                issue_wgrad(tmem, COL_QA, ds, 0, xs, CP, k > 0);                        // rows o < 128
+                issue_wgrad(tmem, COL_QB0, xs, 0, ds + 16 * TILE_CH, 32, k > 0);         // rows o >= 128, i < 128
+                issue_wgrad(tmem, COL_QB1, xs, 16, ds + 16 * TILE_CH, 32, k > 0);        // rows o >= 128, i >= 128
+                mma_commit(&bar_q[k & 1]);
+            }
+            mbits = mnext;
+        }
+        mbar_wait(&bar_q[(mine - 1) & 1], uint32_t((mine - 1) >> 1) & 1u);
+        tc_fence_after_sync();
+        const int C = a.C;
+        for (int ch = 0; ch < HALF_CH; ++ch) {
+            const int n0 = HALF_COLS * half + ch * 8;
+            float d[8];
+            tmem_ld8(tmem_addr(tmem, lane_base, COL_QA + n0), d);
+            if (row < C) {
+                red_add_v4(a.ws.q + size_t(row) * CP + n0, d[0], d[1], d[2], d[3]);
+                red_add_v4(a.ws.q + size_t(row) * CP + n0 + 4, d[4], d[5], d[6], d[7]);
+            }
+        }
+        for (int blk = 0; blk < 2; ++blk) {
+            float d[8];
+            tmem_ld8(tmem_addr(tmem, lane_base, (blk == 0 ? COL_QB0 : COL_QB1) + 8 * half), d);
+            const int i = blk * 128 + row;
+            if (i < CP) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int o = 128 + 8 * half + e;
+                    if (o < C) atomicAdd(a.ws.q + size_t(o) * CP + i, d[e]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
