@@ -659,7 +659,7 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         const size_t stream_smem = 2 * size_t(A_BYTES) + 3 * g_bytes + A_BYTES + wt + 128;
         if (stream_smem <= kMaxSmem) {
             if ((ce2 = cudaFuncSetAttribute(tc_q_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream_smem))) != cudaSuccess) return int(ce2);
-            tc_q_stream_kernel<<<grid, NTH, stream_smem, st>>>(a); count_launch();
+            tc_q_stream_kernel<<<grid, QS_THREADS, stream_smem, st>>>(a); count_launch();
         }
         else if (wt + 3 * per_stage + 64 <= kMaxSmem) FVAE_LAUNCH_Q(3);
         else if (wt + 2 * per_stage + 64 <= kMaxSmem) FVAE_LAUNCH_Q(2);

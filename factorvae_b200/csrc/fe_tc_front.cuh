@@ -27,25 +27,14 @@ __device__ __forceinline__ void copy_image(unsigned char* dst, const void* src, 
     for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
 }
 
-// row GEMM: D[128 x N] (tmem column dcol) = A(K-major tile, 128 rows) . B(K-major image, brows rows)^T over k16 steps
+// row GEMM / weight-gradient GEMM issue loops: tc_sm100.cuh (issue_row_gemm_acc / issue_wgrad_acc)
 __device__ __forceinline__ void issue_row_gemm(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t b_addr, uint32_t brows,
                                                uint32_t N, int k16) {
-    const uint32_t idesc = make_idesc_bf16(TM, N, false, false);
-    for (int ks = 0; ks < k16; ++ks) {
-        const uint64_t ad = make_smem_desc(a_addr + ks * 2 * TILE_CH, TILE_CH, 128);
-        const uint64_t bd = make_smem_desc(b_addr + ks * 2 * (brows * 16), brows * 16, 128);
-        mma_bf16_ss(tmem + dcol, ad, bd, idesc, ks > 0);
-    }
+    issue_row_gemm_acc(tmem, dcol, a_addr, b_addr, brows, N, k16, false);
 }
-// weight-gradient GEMM: D[128 x N] (+)= A^T . B with A, B 128-row tiles read MN-major; A's M block starts at chunk a_chunk0
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t a_chunk0, uint32_t b_addr,
                                             uint32_t N, bool accumulate) {
-    const uint32_t idesc = make_idesc_bf16(TM, N, true, true);
-    for (int ks = 0; ks < TM / 16; ++ks) {
-        const uint64_t ad = make_smem_desc(a_addr + a_chunk0 * TILE_CH + ks * 256, 128, TILE_CH);
-        const uint64_t bd = make_smem_desc(b_addr + ks * 256, 128, TILE_CH);
-        mma_bf16_ss(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
-    }
+    issue_wgrad_acc(tmem, dcol, a_addr, a_chunk0, b_addr, N, accumulate);
 }
 
 // ---- staging of raw panel rows ------------------------------------------------------------------------------
@@ -694,7 +683,8 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_from_tiles_kernel(ItemArgs a) {
 // copies (complete_tx on mbarriers): dGI three items ahead (it gates du), xhat as soon as the Q MMAs of the item that
 // used the stage have completed (it is only needed by Q, one and a half iterations later).  du(k+1) is issued in front
 // of Q(k), so the dpre epilogue of item k+1 overlaps the Q MMAs of item k.  Used when the buffers fit (NC <= 96).
-__global__ void __launch_bounds__(NTH, 1) tc_q_stream_kernel(ItemArgs a) {
+constexpr int QS_THREADS = NTH + 32;          // 512 epilogue threads + one warp that feeds the stages and issues the UMMAs
+__global__ void __launch_bounds__(QS_THREADS, 1) tc_q_stream_kernel(ItemArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
     const int NC = a.NC, NCH = NC / 8;
@@ -708,10 +698,12 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_stream_kernel(ItemArgs a) {
     uint64_t* full_g = bars + 2;        // [3]
     uint64_t* bar_du = bars + 5;
     uint64_t* bar_q = bars + 6;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* dpre_ready = bars + 8;    // all epilogue threads have written their part of the dpre tile (and read du)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const bool issuer = warp == NTH / 32;
     copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
-    for (uint32_t i = tid; i < (2 * A_BYTES + 3 * g_bytes + A_BYTES) / 16; i += NTH) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    for (uint32_t i = tid; i < (2 * A_BYTES + 3 * g_bytes + A_BYTES) / 16; i += QS_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1); mbar_init(dpre_ready, NTH); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     fence_async_smem();
     tc_fence_before_sync();
@@ -737,21 +729,40 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_stream_kernel(ItemArgs a) {
         issue_row_gemm(tmem, COL_DU, smem_u32(sG + (k % 3) * g_bytes), smem_u32(sWihT), CP, CP, NC / 16);
         mma_commit(bar_du);
     };
-    if (mine > 0) {
-        if (tid == 0) {
+    if (mine > 0 && issuer) {
+        if ((tid & 31) == 0) {
             load_g(0); if (mine > 1) load_g(1); if (mine > 2) load_g(2);
             load_x(0); if (mine > 1) load_x(1);
             tc_fence_after_sync();
             issue_du(0);
+            for (int64_t k = 0; k < mine; ++k) {
+                const bool has_next = k + 1 < mine;
+                mbar_wait(bar_du, uint32_t(k) & 1u);           // du(k) done: its dGI stage is free
+                if (k + 3 < mine) load_g(k + 3);
+                if (k > 0) {                                   // Q(k-1) done: xhat stage (k-1)&1 is free
+                    mbar_wait(&bar_q[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u);
+                    if (has_next) load_x(k + 1);
+                }
+                mbar_wait(dpre_ready, uint32_t(k) & 1u);       // dpre(k) is in shared memory, du(k) has been read out of TMEM
+                tc_fence_after_sync();
+                if (has_next) issue_du(k + 1);                 // in front of Q(k)
+                mbar_wait(&full_x[k & 1], uint32_t(k >> 1) & 1u);
+                const uint32_t xs = smem_u32(sX + (k & 1) * A_BYTES), ds = smem_u32(sD);
+                issue_wgrad(tmem, COL_QA, ds, 0, xs, CP, k > 0);                        // rows o < 128
+                issue_wgrad(tmem, COL_QB0, xs, 0, ds + 16 * TILE_CH, 32, k > 0);         // rows o >= 128, i < 128
+                issue_wgrad(tmem, COL_QB1, xs, 16, ds + 16 * TILE_CH, 32, k > 0);        // rows o >= 128, i >= 128
+                mma_commit(&bar_q[k & 1]);
+            }
         }
+        __syncwarp();
+    } else if (mine > 0) {
         unsigned long long mbits = a.ws.mask[size_t(blockIdx.x) * 4 * TM + half * TM + row];
         for (int64_t k = 0; k < mine; ++k) {
             const bool has_next = k + 1 < mine;
             unsigned long long mnext = 0ull;
             if (has_next) mnext = a.ws.mask[size_t(blockIdx.x + (k + 1) * G) * 4 * TM + half * TM + row];
-            mbar_wait(bar_du, uint32_t(k) & 1u);               // du(k) is in TMEM; the dGI stage of item k is free
+            mbar_wait(bar_du, uint32_t(k) & 1u);               // du(k) is in TMEM
             tc_fence_after_sync();
-            if (tid == 0 && k + 3 < mine) load_g(k + 3);
             uint4 pk[HALF_CH];
 #pragma unroll
             for (int ch = 0; ch < HALF_CH; ++ch) {
@@ -761,25 +772,12 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_stream_kernel(ItemArgs a) {
                 for (int e = 0; e < 8; ++e) d[e] *= ((mbits >> (ch * 8 + e)) & 1ull) ? 1.f : kLeakySlope;
                 pk[ch] = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
             }
-            if (k > 0) {                                       // Q(k-1) done: the dpre tile and xhat stage (k-1)&1 are free
-                mbar_wait(&bar_q[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u);
-                if (tid == 0 && has_next) load_x(k + 1);
-            }
+            if (k > 0) mbar_wait(&bar_q[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u);     // Q(k-1) done: the dpre tile is free
 #pragma unroll
             for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sD + tile_off(TM, row, HALF_CH * half + ch)) = pk[ch];
             fence_async_smem();
             tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                if (has_next) issue_du(k + 1);                 // in front of Q(k): COL_DU was read before the barrier
-                mbar_wait(&full_x[k & 1], uint32_t(k >> 1) & 1u);
-                const uint32_t xs = smem_u32(sX + (k & 1) * A_BYTES), ds = smem_u32(sD);
-                issue_wgrad(tmem, COL_QA, ds, 0, xs, CP, k > 0);                        // rows o < 128
-                issue_wgrad(tmem, COL_QB0, xs, 0, ds + 16 * TILE_CH, 32, k > 0);         // rows o >= 128, i < 128
-                issue_wgrad(tmem, COL_QB1, xs, 16, ds + 16 * TILE_CH, 32, k > 0);        // rows o >= 128, i >= 128
-                mma_commit(&bar_q[k & 1]);
-            }
+            mbar_arrive(dpre_ready);
             mbits = mnext;
         }
         mbar_wait(&bar_q[(mine - 1) & 1], uint32_t((mine - 1) >> 1) & 1u);

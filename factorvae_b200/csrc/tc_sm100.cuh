@@ -175,24 +175,30 @@ __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, uint32_t lane, uint
 constexpr uint32_t kTileRows = 128;                 // UMMA M = TMEM lanes
 constexpr uint32_t kTileChunk = kTileRows * 16;     // bytes of one 8-column chunk of a 128-row tile
 
+// The descriptors of consecutive k steps differ only in the start-address field (bits [0,14), units of 16 bytes): build
+// them once and step with one 64-bit add per operand (shared memory is < 256 KB, so the field never carries out).
 // row GEMM: D[128 x N] (tmem column dcol) (+)= A(K-major tile, 128 rows) . B(K-major image, brows rows)^T over k16 steps
 __device__ __forceinline__ void issue_row_gemm_acc(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t b_addr, uint32_t brows,
                                                    uint32_t N, int k16, bool accumulate) {
     const uint32_t idesc = make_idesc_bf16(kTileRows, N, false, false);
+    uint64_t ad = make_smem_desc(a_addr, kTileChunk, 128);
+    uint64_t bd = make_smem_desc(b_addr, brows * 16, 128);
+    const uint64_t astep = (2 * kTileChunk) >> 4, bstep = (2 * brows * 16) >> 4;
     for (int ks = 0; ks < k16; ++ks) {
-        const uint64_t ad = make_smem_desc(a_addr + ks * 2 * kTileChunk, kTileChunk, 128);
-        const uint64_t bd = make_smem_desc(b_addr + ks * 2 * (brows * 16), brows * 16, 128);
         mma_bf16_ss(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        ad += astep; bd += bstep;
     }
 }
 // weight-gradient GEMM: D[128 x N] (+)= A^T . B with A, B 128-row tiles read MN-major; A's M block starts at chunk a_chunk0
 __device__ __forceinline__ void issue_wgrad_acc(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t a_chunk0, uint32_t b_addr,
                                                 uint32_t N, bool accumulate) {
     const uint32_t idesc = make_idesc_bf16(kTileRows, N, true, true);
+    uint64_t ad = make_smem_desc(a_addr + a_chunk0 * kTileChunk, 128, kTileChunk);
+    uint64_t bd = make_smem_desc(b_addr, 128, kTileChunk);
+#pragma unroll
     for (int ks = 0; ks < int(kTileRows) / 16; ++ks) {
-        const uint64_t ad = make_smem_desc(a_addr + a_chunk0 * kTileChunk + ks * 256, 128, kTileChunk);
-        const uint64_t bd = make_smem_desc(b_addr + ks * 256, 128, kTileChunk);
         mma_bf16_ss(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        ad += 256 >> 4; bd += 256 >> 4;
     }
 }
 
