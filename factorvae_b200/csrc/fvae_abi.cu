@@ -173,7 +173,9 @@ int run_forward(const fvae_shape* shape, const fvae_panel* x, const float* y, co
     if (predict) flags &= ~FVAE_FLAG_TRAIN;          // prediction runs the modules in eval() (utils.py:76)
     HeadsArgs a = make_heads_args(*shape, W, y, date_ptr, *noise, flags, predict, *out, hw);
     const FeDims fd{shape->S, shape->T, shape->C, shape->H};
+    a.use_tc = (precision == FVAE_PREC_BF16_TC) ? 1 : 0;
     if ((rc = heads_prep(a, false, st)) != 0) return rc;
+    if (a.use_tc && heads_tc_supported(shape->H, shape->K, shape->M) && (rc = heads_tc_prep(a, st)) != 0) return rc;
     if ((rc = fe_forward_any(fd, *x, fw, precision, W.e, W.fe_ws, st)) != 0) return rc;
     if ((rc = heads_forward(a, st)) != 0) return rc;
     if (!predict && (rc = loss_reduce(out->date_loss, shape->B, out->loss, st)) != 0) return rc;

@@ -896,6 +896,7 @@ int loss_reduce(const float* date_loss, int B, float* loss, cudaStream_t stream)
 static int pick_hp(int H) { return H <= 20 ? 20 : (H <= 32 ? 32 : (H <= 48 ? 48 : 64)); }
 
 int heads_forward(const HeadsArgs& a, cudaStream_t stream) {
+    if (a.use_tc && heads_tc_supported(a.H, a.K, a.M)) return heads_tc_forward(a, stream);
     const int HP = pick_hp(a.H);
     const size_t smem = fwd_smem_bytes(HP, a.H, a.K, a.M);
     int rc;

@@ -99,6 +99,7 @@ __host__ __device__ inline TcCols tc_cols(int H, int K, int M) {
 inline bool heads_tc_supported(int H, int K, int M) { return M == 128 && H <= 31 && K <= 32; }
 int64_t heads_tc_image_bytes(int H, int K, int M, int which);     // which: 1 = forward-product image, 2 = dE image
 int heads_tc_prep(const HeadsArgs& a, cudaStream_t stream);        // builds the images (after heads_prep)
+int heads_tc_forward(const HeadsArgs& a, cudaStream_t stream);       // forward of the heads (images must be built)
 int heads_tc_sweep(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t stream);
 
 // all launchers are asynchronous on `stream` and return a cudaError_t as int

@@ -503,6 +503,436 @@ __global__ void __launch_bounds__(TNT_ALL, 1) heads_tc_sweep_kernel(HeadsArgs a,
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+
+// =================================================================================================================
+// Forward of the heads on tcgen05 (FVAE_PREC_BF16_TC, M == 128, H <= 31, K <= 32).  One CTA walks whole dates.
+//   loop 1 over the 128-stock tiles of the date:  F_enc^T = Wp . E^T  (TMEM lane = portfolio j, column = stock)
+//                                                 F_row   = E . [G; Wb; Wa]^T  (lane = stock)
+//        group A (thread = portfolio column): online softmax over the stocks -> max, sum, y_p
+//        group B (thread = stock): attention scores -> per-head maximum (the NaN/Inf guard rides in it as +inf)
+//   posterior (mapping layer), then loop 2:
+//        group A (thread = stock): attention weights p = exp(s - max) -> bf16 tile P, per-head sums;
+//                                  pooled += P^T . E as a UMMA whose accumulator stays in TMEM for the date
+//        group B (thread = stock): decoder (alpha / beta heads, mu_y, sigma_y, sample, squared error, the column sums
+//                                  backward needs)
+//   prior head, KL, loss.  FactorVAE.prediction: the decoder runs in a third loop, after the prior.
+// Same image (t_b1: hi | lo rows [Wp; G; Wb; Wa] with the bias column) as the backward sweep.
+constexpr int FNT = 256;
+constexpr uint32_t kFColEnc = 0, kFColRow = 128, kFColPool = 224;      // TMEM columns (256 allocated)
+
+struct FwdSmem {
+    uint32_t et, b1s, pt, ys, yp, muz, sgz, mupr, sgpr, pooled, ctx, hm, attm, attl, c1a, c1b, red, bad, gbad, bar, slot, total;
+};
+__host__ __device__ inline FwdSmem fwd_layout(int M, const TcCols& tcg) {
+    FwdSmem s; uint32_t p = 0;
+    auto take = [&](uint32_t n) { uint32_t r = p; p += (n + 127u) & ~127u; return r; };
+    s.et = take(2 * 8 * kTileChunk);
+    s.pt = take(16 * kTileChunk);           // P tile (Kp/8 chunks written; the UMMA M block spans 16)
+    s.b1s = take(8u * tcg.NS * 16u);
+    s.ys = take(128 * 4);
+    s.yp = take(uint32_t(M) * 4);
+    s.muz = take(32 * 4); s.sgz = take(32 * 4); s.mupr = take(32 * 4); s.sgpr = take(32 * 4);
+    s.pooled = take(32 * 32 * 4); s.ctx = take(32 * 32 * 4); s.hm = take(32 * 32 * 4);
+    s.attm = take(32 * 4); s.attl = take(32 * 4); s.c1a = take(32 * 4); s.c1b = take(32 * 4);
+    s.red = take(32 * 4); s.bad = take(32 * 4); s.gbad = take(32 * 4);
+    s.bar = take(16); s.slot = take(16);
+    s.total = p;
+    return s;
+}
+
+template <typename Op>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane, Op op) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float keep = up ? v[i + o] : v[i];
+            const float send = up ? v[i] : v[i + o];
+            v[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, o));
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(FNT, 2) heads_tc_fwd_kernel(HeadsArgs a, TcCols tcg) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int H = a.H, K = a.K, M = a.M, NS = tcg.NS, Kp = tcg.Kp, Hp8 = tcg.Hp8;
+    const int tid = threadIdx.x, row = tid & 127, grp = tid >> 7, warp = tid >> 5, lane = tid & 31;
+    const FwdSmem L = fwd_layout(M, tcg);
+    uint8_t* Et = smem + L.et;
+    uint8_t* Pt = smem + L.pt;
+    uint8_t* B1s = smem + L.b1s;
+    float* ys = reinterpret_cast<float*>(smem + L.ys);
+    float* yp = reinterpret_cast<float*>(smem + L.yp);
+    float* muz = reinterpret_cast<float*>(smem + L.muz);
+    float* sgz = reinterpret_cast<float*>(smem + L.sgz);
+    float* mupr = reinterpret_cast<float*>(smem + L.mupr);
+    float* sgpr = reinterpret_cast<float*>(smem + L.sgpr);
+    float* pooled = reinterpret_cast<float*>(smem + L.pooled);   // [k][h], row stride H
+    float* ctx = reinterpret_cast<float*>(smem + L.ctx);
+    float* hm = reinterpret_cast<float*>(smem + L.hm);
+    int* attm = reinterpret_cast<int*>(smem + L.attm);           // per-head maximum as float bits (scores are >= 0)
+    float* attl = reinterpret_cast<float*>(smem + L.attl);
+    float* c1a = reinterpret_cast<float*>(smem + L.c1a);
+    float* c1b = reinterpret_cast<float*>(smem + L.c1b);
+    float* red = reinterpret_cast<float*>(smem + L.red);
+    int* bad = reinterpret_cast<int*>(smem + L.bad);
+    int* gbad = reinterpret_cast<int*>(smem + L.gbad);          // collapsed key row of the head is not finite: the guard trips on every date
+    uint64_t* barM = reinterpret_cast<uint64_t*>(smem + L.bar);
+    uint64_t* barP = barM + 1;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(smem + L.slot);
+
+    if (warp == 0) tmem_alloc<256>(slot);
+    if (tid == 0) { mbar_init(barM, 1); mbar_init(barP, 1); mbar_fence_init(); }
+    {
+        const uint4* s1 = static_cast<const uint4*>(a.sv.t_b1);
+        for (int i = tid; i < 8 * NS; i += FNT) reinterpret_cast<uint4*>(B1s)[i] = s1[i];
+        for (int i = tid; i < 16 * 128; i += FNT) reinterpret_cast<uint4*>(Pt)[i] = make_uint4(0, 0, 0, 0);
+        if (tid < 32) {          // the images hold sanitised rows, so a non-finite G_k / c_k has to be remembered here
+            int nb = 0;
+            if (tid < K) {
+                if (!(fabsf(a.sv.cvec[tid]) <= FLT_MAX)) nb = 1;
+                for (int h = 0; h < H; ++h) if (!(fabsf(a.sv.G[size_t(tid) * H + h]) <= FLT_MAX)) nb = 1;
+            }
+            gbad[tid] = nb;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *slot;
+    const uint32_t lane_base = tmem + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t et_addr = smem_u32(Et), pt_addr = smem_u32(Pt), b1s_addr = smem_u32(B1s);
+    const float inv_tau = 1.f / sqrtf(float(H) + 1e-6f);
+    const bool train_path = !a.predict;
+    uint32_t phM = 0, phP = 0;
+
+    // D[dcol..) = A . B^T with both operands split hi | lo (chunks 0-3 | 4-7, K = 32): hi.hi + lo.hi + hi.lo
+    auto issue_split = [&](uint32_t a_addr, uint32_t a_lbo, uint32_t b_addr, uint32_t b_lbo, uint32_t N, uint32_t dcol) {
+        const uint32_t idesc = make_idesc_bf16(kTileRows, N, false, false);
+        auto mm = [&](uint32_t ac, uint32_t bc, uint32_t acc) {
+            mma_bf16_ss(tmem + dcol, make_smem_desc(a_addr + ac * a_lbo, a_lbo, 128), make_smem_desc(b_addr + bc * b_lbo, b_lbo, 128), idesc, acc);
+        };
+        mm(0, 0, 0); mm(2, 2, 1); mm(4, 0, 1); mm(6, 2, 1); mm(0, 4, 1); mm(2, 6, 1);
+    };
+
+    for (int d = blockIdx.x; d < a.B; d += gridDim.x) {
+        const int p0 = a.date_ptr[d], n = a.date_ptr[d + 1] - p0;
+        if (n <= 0) { if (tid == 0 && a.out.date_loss) a.out.date_loss[d] = nanf(""); continue; }
+        const int ntile = (n + 127) / 128;
+        const float coefN = 2.f / (float(n) * float(a.B));
+        if (tid < 32) { attm[tid] = 0; attl[tid] = 0.f; c1a[tid] = 0.f; c1b[tid] = 0.f; bad[tid] = 0; }
+        float m_e = -INFINITY, l_e = 0.f, acc_e = 0.f;          // group A in loop 1: online softmax state of portfolio column `row`
+        float rec_part = 0.f;
+        __syncthreads();
+
+        auto load_e = [&](int t, float (&v)[16]) {               // my 16 columns [16 grp, 16 grp + 16) of my row (ones column at H)
+            const int i = t * 128 + row;
+            const bool valid = i < n;
+            const float* src = a.e + size_t(p0 + i) * H;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int h = grp * 16 + q;
+                v[q] = (valid && h < H) ? src[h] : ((valid && h == H) ? 1.f : 0.f);
+            }
+        };
+        auto store_e = [&](int buf, const float (&v)[16]) {
+            uint8_t* eb = Et + buf * 8 * kTileChunk;
+            float lo8[8], hi8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { lo8[q] = v[q]; hi8[q] = v[8 + q]; }
+            split_store8(eb + tile_off(128, row, 2 * grp), eb + tile_off(128, row, 4 + 2 * grp), lo8);
+            split_store8(eb + tile_off(128, row, 2 * grp + 1), eb + tile_off(128, row, 4 + 2 * grp + 1), hi8);
+        };
+        // attention score of (my stock, head k) from the accumulator value: relu(dropout(f / tau)); non-finite -> +inf
+        auto att_score = [&](float f, int u, int k) {
+            const float x = relu_nan(f * inv_tau * keep_factor(a, u, k));
+            return (fabsf(x) <= FLT_MAX) ? x : INFINITY;
+        };
+
+        auto tile_loop = [&](bool do_enc, bool do_attmax, bool do_attp, bool do_dec) {
+            float ev[16];
+            load_e(0, ev);
+            for (int t = 0; t < ntile; ++t) {
+                store_e(t & 1, ev);
+                if (tid < 128) ys[tid] = (train_path && t * 128 + tid < n) ? a.y[p0 + t * 128 + tid] : 0.f;
+                if (do_attp && t > 0) { mbar_wait(barP, phP); phP ^= 1; }          // pooled MMA of the previous tile: P tile free
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    const uint32_t ea = et_addr + (t & 1) * 8 * kTileChunk;
+                    if (do_enc) issue_split(b1s_addr, uint32_t(NS) * 16u, ea, kTileChunk, 128, kFColEnc);
+                    issue_split(ea, kTileChunk, b1s_addr + 128 * 16, uint32_t(NS) * 16u, uint32_t(NS - 128), kFColRow);
+                    mma_commit(barM);
+                }
+                if (t + 1 < ntile) load_e(t + 1, ev);
+                mbar_wait(barM, phM); phM ^= 1;
+                tc_fence_after_sync();
+                const int nv = min(128, n - t * 128);
+                const int i = t * 128 + row;
+                const bool valid = i < n;
+                const int u = p0 + i;
+                if (grp == 0) {
+                    if (do_enc) {        // thread = portfolio column `row`: columns of my TMEM lane are the stocks of the tile
+                        float tmax = -INFINITY;
+                        for (int g16 = 0; g16 * 16 < nv; ++g16) {
+                            float f[16];
+                            tmem_ld16(lane_base + kFColEnc + uint32_t(g16 * 16), f);
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) tmax = fmaxf(tmax, (g16 * 16 + q < nv) ? f[q] : -INFINITY);
+                        }
+                        if (tmax > m_e) {
+                            const float sc = ex2_fast((m_e - tmax) * kL2E);
+                            l_e *= sc; acc_e *= sc; m_e = tmax;
+                        }
+                        const float mb = -m_e * kL2E;
+                        for (int g16 = 0; g16 * 16 < nv; ++g16) {
+                            float f[16];
+                            tmem_ld16(lane_base + kFColEnc + uint32_t(g16 * 16), f);
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const float pz = (g16 * 16 + q < nv) ? ex2_fast(fmaf(f[q], kL2E, mb)) : 0.f;
+                                l_e += pz;
+                                acc_e = fmaf(pz, ys[g16 * 16 + q], acc_e);
+                            }
+                        }
+                    }
+                    if (do_attp) {       // thread = stock: attention weights (unnormalised) -> P tile, per-head sums
+                        float r[32];
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) {
+                            float f[8], pz[8];
+                            if (kc < Kp / 8) tmem_ld8(lane_base + kFColRow + uint32_t(kc * 8), f);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int k = kc * 8 + q;
+                                float pv = 0.f;
+                                if (kc < Kp / 8 && valid && k < K && !bad[k]) pv = expf(att_score(f[q], u, k) - __int_as_float(attm[k]));
+                                pz[q] = pv; r[k] = pv;
+                            }
+                            if (kc < Kp / 8) store8(Pt + tile_off(128, row, kc), pz);
+                        }
+                        const float sl = warp_transpose_reduce(r, lane, [](float x, float y) { return x + y; });
+                        atomicAdd(attl + lane, sl);
+                    }
+                } else {
+                    if (do_attmax) {     // thread = stock: per-head maximum of the scores over the stocks
+                        float r[32];
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) {
+                            float f[8];
+                            if (kc < Kp / 8) tmem_ld8(lane_base + kFColRow + uint32_t(kc * 8), f);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int k = kc * 8 + q;
+                                r[k] = (kc < Kp / 8 && valid && k < K) ? att_score(f[q], u, k) : 0.f;
+                            }
+                        }
+                        const float mx = warp_transpose_reduce(r, lane, [](float x, float y) { return fmaxf(x, y); });
+                        atomicMax(attm + lane, __float_as_int(mx));
+                    }
+                    if (do_dec) {        // thread = stock: decoder (module.py:107-123)
+                        float bt[32];
+                        float mu = 0.f, var = 0.f;
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) {
+                            float f[8];
+                            if (kc < Kp / 8) tmem_ld8(lane_base + kFColRow + uint32_t(Kp + kc * 8), f);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int k = kc * 8 + q;
+                                const float b = (kc < Kp / 8 && k < K) ? f[q] : 0.f;
+                                bt[k] = b;
+                                if (k < K) { mu = fmaf(b, muz[k], mu); var = fmaf(b * b, sgz[k] * sgz[k], var); }
+                            }
+                        }
+                        float amu = a.w.bam[0], asp = a.w.bas[0];
+#pragma unroll
+                        for (int jc = 0; jc < 4; ++jc) {
+                            float f[8];
+                            if (jc < Hp8 / 8) tmem_ld8(lane_base + kFColRow + uint32_t(2 * Kp + jc * 8), f);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int j = jc * 8 + q;
+                                if (jc < Hp8 / 8 && j < H) {
+                                    const float ha = lrelu(f[q]);
+                                    amu = fmaf(a.w.wam[j], ha, amu);
+                                    asp = fmaf(a.w.was[j], ha, asp);
+                                }
+                            }
+                        }
+                        float dmy = 0.f, dvv = 0.f;
+                        if (valid) {
+                            const float asig = softplus(asp);
+                            mu += amu;
+                            const float sy = sqrtf(var + asig * asig + 1e-6f);
+                            const float ep = eps_of(a, u);
+                            const float yh = fmaf(ep, sy, mu);
+                            a.out.yhat[u] = yh; a.out.mu_y[u] = mu; a.out.sigma_y[u] = sy;
+                            if (train_path) {
+                                const float dlt = yh - ys[row];
+                                rec_part = fmaf(dlt, dlt, rec_part);
+                                dmy = coefN * dlt;
+                                dvv = dmy * ep / (2.f * sy);
+                            }
+                        }
+                        if (train_path) {        // column sums for backward: sum_i beta_ik dmu_y_i, sum_i beta_ik^2 dvar_i
+                            float r[32];
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) r[k] = bt[k] * dmy;
+                            const float s1 = warp_transpose_reduce(r, lane, [](float x, float y) { return x + y; });
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) r[k] = bt[k] * bt[k] * dvv;
+                            const float s2 = warp_transpose_reduce(r, lane, [](float x, float y) { return x + y; });
+                            atomicAdd(c1a + lane, s1);
+                            atomicAdd(c1b + lane, s2);
+                        }
+                    }
+                }
+                if (do_attp) fence_async_smem();
+                tc_fence_before_sync();
+                __syncthreads();
+                if (do_attp && tid == 0) {
+                    tc_fence_after_sync();
+                    issue_wgrad_acc(tmem, kFColPool, pt_addr, 0, et_addr + (t & 1) * 8 * kTileChunk, kHK, t > 0);
+                    mma_commit(barP);
+                }
+            }
+            if (do_attp) { mbar_wait(barP, phP); phP ^= 1; tc_fence_after_sync(); }
+        };
+
+        // ---- loop 1: softmax statistics
+        tile_loop(train_path, true, false, false);
+        if (grp == 0 && train_path) {
+            a.sv.enc_m[size_t(d) * M + row] = m_e;
+            a.sv.enc_l[size_t(d) * M + row] = l_e;
+            const float v = acc_e / l_e;
+            yp[row] = v;
+            a.sv.yp[size_t(d) * M + row] = v;
+        }
+        if (tid < 32) {
+            const float mk = __int_as_float(attm[tid]);
+            const int bd = (tid < K && (gbad[tid] || !(fabsf(mk) <= FLT_MAX))) ? 1 : 0;
+            bad[tid] = bd;
+            if (bd) attm[tid] = 0;
+        }
+        __syncthreads();
+        // ---- posterior (module.py:48-49) and the :117 clamp: 8 threads per factor
+        if (train_path) {
+            const int k = tid >> 3, part = tid & 7;
+            float mu = 0.f, pre = 0.f;
+            if (k < K) {
+                const float* wm = a.w.Wmu + size_t(k) * M;
+                const float* ws = a.w.Wsig + size_t(k) * M;
+                for (int j = part; j < M; j += 8) { mu = fmaf(wm[j], yp[j], mu); pre = fmaf(ws[j], yp[j], pre); }
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) { mu += __shfl_xor_sync(0xffffffffu, mu, o); pre += __shfl_xor_sync(0xffffffffu, pre, o); }
+            if (k < K && part == 0) {
+                mu += a.w.bmu[k]; pre += a.w.bsig[k];
+                float sg = softplus(pre);
+                const int cl = (sg == 0.f);
+                if (cl) sg = kSigmaFloor;
+                muz[k] = mu; sgz[k] = sg;
+                a.out.mu_post[size_t(d) * K + k] = mu;
+                a.out.sigma_post[size_t(d) * K + k] = sg;
+                a.sv.pre_sg_post[size_t(d) * K + k] = pre;
+                a.sv.clamp_post[size_t(d) * K + k] = cl;
+            }
+        }
+        __syncthreads();
+        // ---- loop 2: attention weights + pooled hidden state (and the decoder when the posterior feeds it)
+        tile_loop(false, false, true, train_path);
+        if (warp == 0) {                                         // pooled: TMEM lane = head k, column = h
+            float v[32];
+            {
+                float t8[8];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    tmem_ld8(lane_base + kFColPool + 8u * q4, t8);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q4 * 8 + q] = t8[q];
+                }
+            }
+            const int k = lane;
+            if (k < K) {
+                const float l = attl[k];
+                const bool bd = bad[k] != 0;
+                a.sv.att_m[size_t(d) * K + k] = __int_as_float(attm[k]);
+                a.sv.att_l[size_t(d) * K + k] = l;
+                a.sv.bad[size_t(d) * K + k] = bd ? 1 : 0;
+                const float inv = bd ? 0.f : 1.f / l;
+#pragma unroll
+                for (int h = 0; h < 32; ++h)
+                    if (h < H) {
+                        const float pv = bd ? 0.f : v[h] * inv;
+                        pooled[k * H + h] = pv;
+                        a.sv.pooled[(size_t(d) * K + k) * H + h] = pv;
+                    }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+        // ---- prior: ctx_k = Wv_k pooled_k + bv_k (zeros if the guard tripped), shared MLP head (module.py:169-188)
+        for (int idx = tid; idx < K * H; idx += FNT) {
+            const int k = idx / H, j = idx % H;
+            float v = 0.f;
+            if (!bad[k]) {
+                const float* wv = a.w.Wv + (size_t(k) * H + j) * H;
+                v = a.w.bv[size_t(k) * H + j];
+                for (int h = 0; h < H; ++h) v = fmaf(wv[h], pooled[k * H + h], v);
+            }
+            ctx[idx] = v;
+            a.sv.ctx[size_t(d) * K * H + idx] = v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < K * H; idx += FNT) {
+            const int k = idx / H, j = idx % H;
+            float v = a.w.bl[j];
+            const float* wl = a.w.Wl + size_t(j) * H;
+            for (int h = 0; h < H; ++h) v = fmaf(wl[h], ctx[k * H + h], v);
+            a.sv.hm_pre[size_t(d) * K * H + idx] = v;
+            hm[idx] = lrelu(v);
+        }
+        __syncthreads();
+        for (int k = tid; k < K; k += FNT) {
+            float mu = a.w.bpm[0], pre = a.w.bps[0];
+            for (int j = 0; j < H; ++j) { mu = fmaf(a.w.wpm[j], hm[k * H + j], mu); pre = fmaf(a.w.wps[j], hm[k * H + j], pre); }
+            float sg = softplus(pre);
+            const int cl = (sg == 0.f);
+            if (cl) sg = kSigmaFloor;                          // module.py:264-265 (and :117 in prediction)
+            mupr[k] = mu; sgpr[k] = sg;
+            a.out.mu_prior[size_t(d) * K + k] = mu;
+            a.out.sigma_prior[size_t(d) * K + k] = sg;
+            a.sv.pre_sg_prior[size_t(d) * K + k] = pre;
+            a.sv.clamp_prior[size_t(d) * K + k] = cl;
+            if (a.predict) { muz[k] = mu; sgz[k] = sg; }
+        }
+        __syncthreads();
+        if (a.predict) {
+            tile_loop(false, false, false, true);              // decoder fed by the prior (module.py:273-278)
+            __syncthreads();
+            continue;
+        }
+        if (tid < K) { a.sv.c1_mu[size_t(d) * K + tid] = c1a[tid]; a.sv.c1_sg[size_t(d) * K + tid] = c1b[tid]; }
+        const float rec = block_sum(rec_part, red) / float(n);   // F.mse_loss: mean over stocks
+        float klp = 0.f;
+        for (int k = tid; k < K; k += FNT) {                     // module.py:247
+            const float m1 = muz[k], s1 = sgz[k], m2 = mupr[k], s2 = sgpr[k];
+            klp += logf(s2 / s1) + (s1 * s1 + (m1 - m2) * (m1 - m2)) / (2.f * s2 * s2) - 0.5f;
+        }
+        const float kl = block_sum(klp, red);
+        if (tid == 0) a.out.date_loss[d] = rec + kl;
+        __syncthreads();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 }  // namespace
 
 int64_t heads_tc_image_bytes(int H, int K, int M, int which) {
@@ -516,6 +946,19 @@ int heads_tc_prep(const HeadsArgs& a, cudaStream_t stream) {
     return int(cudaGetLastError());
 }
 
+int heads_tc_forward(const HeadsArgs& a, cudaStream_t stream) {
+    const TcCols c = tc_cols(a.H, a.K, a.M);
+    const FwdSmem L = fwd_layout(a.M, c);
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cudaError_t e = cudaFuncSetAttribute(heads_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.total));
+    if (e != cudaSuccess) return int(e);
+    const int grid = a.B < 2 * sms ? a.B : 2 * sms;
+    heads_tc_fwd_kernel<<<grid, FNT, L.total, stream>>>(a, c); count_launch();
+    return int(cudaGetLastError());
+}
+
 int heads_tc_sweep(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t stream) {
     const TcCols c = tc_cols(a.H, a.K, a.M);
     const SweepSmem L = sweep_layout(a.M, c);
@@ -524,8 +967,6 @@ int heads_tc_sweep(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t 
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     cudaError_t e = cudaFuncSetAttribute(heads_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.total));
     if (e != cudaSuccess) return int(e);
-    int rc = heads_tc_prep(a, stream);
-    if (rc != 0) return rc;
     heads_tc_sweep_kernel<<<sms, TNT_ALL, L.total, stream>>>(a, g, dE, c); count_launch();
     return int(cudaGetLastError());
 }
