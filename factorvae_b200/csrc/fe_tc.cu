@@ -671,16 +671,12 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     {   // dWih from the u tiles saved by the forward kernel (the panel is not touched)
         const size_t per_stage = size_t(NC / 8) * TILE_CH + A_BYTES;
         cudaError_t ce2;
-        if (3 * per_stage + 64 <= kMaxSmem) {
-            const size_t smemw = 3 * per_stage + 64;
-            if ((ce2 = cudaFuncSetAttribute(tc_wih_from_u_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemw))) != cudaSuccess) return int(ce2);
-            tc_wih_from_u_kernel<3><<<grid, WIH_THREADS, smemw, st>>>(a); count_launch();
-        } else {
-            const size_t smemw = 2 * per_stage + 64;
-            if (smemw > kMaxSmem) return FVAE_ERR_LIMIT;
-            if ((ce2 = cudaFuncSetAttribute(tc_wih_from_u_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemw))) != cudaSuccess) return int(ce2);
-            tc_wih_from_u_kernel<2><<<grid, WIH_THREADS, smemw, st>>>(a); count_launch();
-        }
+        int nst = int((kMaxSmem - 128) / per_stage);              // as deep a ring as shared memory allows
+        if (nst > 6) nst = 6;
+        if (nst < 1) return FVAE_ERR_LIMIT;
+        const size_t smemw = size_t(nst) * per_stage + 128;
+        if ((ce2 = cudaFuncSetAttribute(tc_wih_from_u_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemw))) != cudaSuccess) return int(ce2);
+        tc_wih_from_u_kernel<<<grid, WIH_THREADS, smemw, st>>>(a, nst); count_launch();
         if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
     }
     PostArgs p{d.C, d.H, NC, w.ln_w, w.ln_b, w.W1, ws.q, ws.dwih, gr};

@@ -430,62 +430,56 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
 // ---- K4b: dWih += dGI^T [u | 1] from the u tiles saved by K1 -- pure streaming: two operand tiles per item arrive by
 // cp.async into a 3-deep ring while the weight-gradient MMAs of older items run; bounded by HBM (61 KB per item).
 constexpr int WIH_THREADS = 256;
-template <int WIH_STAGES>
-__global__ void __launch_bounds__(WIH_THREADS, 1) tc_wih_from_u_kernel(ItemArgs a) {
+__global__ void __launch_bounds__(WIH_THREADS, 1) tc_wih_from_u_kernel(ItemArgs a, int nstages) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int NC = a.NC, NCH = NC / 8;
     const int MBW = NC > 128 ? 2 : 1;
     const uint32_t g_bytes = uint32_t(NCH) * TILE_CH, stage_bytes = g_bytes + A_BYTES;      // [dGI tile | u tile]
-    unsigned char* sRing = smem;                                   // WIH_STAGES x [dGI | u]; the dGI M-block over-read runs into u
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + WIH_STAGES * stage_bytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WIH_STAGES);
-    if (tid == 0) { for (int i = 0; i < WIH_STAGES; ++i) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    unsigned char* sRing = smem;                                   // nstages x [dGI | u]; the dGI M-block over-read runs into u
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRing + uint32_t(nstages) * stage_bytes);   // [nstages] tiles landed (complete_tx)
+    uint64_t* done = full + nstages;                               // [nstages] the UMMAs that read the stage have completed
+    uint64_t* fin = done + nstages;                                // everything issued has completed (one phase: the other
+                                                                   // threads cannot track the per-stage phases they never waited on)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin + 1);
+    if (tid == 0) { for (int i = 0; i < 2 * nstages + 1; ++i) mbar_init(&full[i], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const int64_t nitems = a.NT * a.T, G = gridDim.x;
-    auto issue_loads = [&](int64_t item, int stg) {
-        unsigned char* dst = sRing + uint32_t(stg) * stage_bytes;
-        const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * g_bytes;
-        const unsigned char* usrc = reinterpret_cast<const unsigned char*>(a.ws.u) + size_t(item) * A_BYTES;
-        for (uint32_t i = tid; i < g_bytes / 16; i += WIH_THREADS) cp_async16(smem_u32(dst + i * 16), gsrc + i * 16);
-        for (uint32_t i = tid; i < A_BYTES / 16; i += WIH_THREADS) cp_async16(smem_u32(dst + g_bytes + i * 16), usrc + i * 16);
-        cp_async_commit();
-    };
-    // ring: loads run WIH_STAGES-1 items ahead of the MMAs
-    int64_t next_load = blockIdx.x;
-    for (int sidx = 0; sidx < WIH_STAGES - 1; ++sidx) {
-        if (next_load < nitems) issue_loads(next_load, sidx); else cp_async_commit();
-        next_load += G;
-    }
-    uint32_t phase_bits = 0;           // per-stage mbarrier phases
-    bool started = false;
-    int k = 0;
-    for (int64_t item = blockIdx.x; item < nitems; item += G, ++k) {
-        const int stg = k % WIH_STAGES;
-        // stage (k + STAGES - 1) % STAGES was used by item k-1: its MMAs must be done before it is refilled
-        const int refill = (k + WIH_STAGES - 1) % WIH_STAGES;
-        if (k > 0) { mbar_wait(&bars[refill], (phase_bits >> refill) & 1u); phase_bits ^= 1u << refill; }
-        if (next_load < nitems) issue_loads(next_load, refill); else cp_async_commit();
-        next_load += G;
-        cp_async_wait<WIH_STAGES - 1>();          // the loads of item k have landed
-        fence_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
+    const int64_t mine = nitems > int64_t(blockIdx.x) ? (nitems - 1 - blockIdx.x) / G + 1 : 0;
+    const bool started = mine > 0;
+    // One thread streams everything: bulk copies nstages items ahead, one weight-gradient UMMA group per item.
+    if (tid == 0 && mine > 0) {
+        auto load = [&](int64_t k) {
+            const int stg = int(k % nstages);
+            const int64_t item = int64_t(blockIdx.x) + k * G;
+            unsigned char* dst = sRing + uint32_t(stg) * stage_bytes;
+            mbar_expect_tx(&full[stg], stage_bytes);
+            bulk_g2s(dst, reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * g_bytes, g_bytes, &full[stg]);
+            bulk_g2s(dst + g_bytes, reinterpret_cast<const unsigned char*>(a.ws.u) + size_t(item) * A_BYTES, A_BYTES, &full[stg]);
+        };
+        for (int64_t k = 0; k < mine && k < nstages; ++k) load(k);
+        for (int64_t k = 0; k < mine; ++k) {
+            const int stg = int(k % nstages);
+            mbar_wait(&full[stg], uint32_t(k / nstages) & 1u);
             tc_fence_after_sync();
             const uint32_t base = smem_u32(sRing + uint32_t(stg) * stage_bytes);
-            for (int mb = 0; mb < MBW; ++mb) issue_wgrad(tmem, uint32_t(mb) * CP, base, 16 * mb, base + g_bytes, CP, started);
-            mma_commit(&bars[stg]);
+            for (int mb = 0; mb < MBW; ++mb) issue_wgrad(tmem, uint32_t(mb) * CP, base, 16 * mb, base + g_bytes, CP, k > 0);
+            mma_commit(&done[stg]);
+            if (k >= 1 && k - 1 + nstages < mine) {                // the stage of item k-1 is free once its UMMAs are done
+                const int ps = int((k - 1) % nstages);
+                mbar_wait(&done[ps], uint32_t((k - 1) / nstages) & 1u);
+                load(k - 1 + nstages);
+            }
         }
-        started = true;
+        mma_commit(fin);
     }
-    // drain: the last item's MMAs (commits are ordered, so its barrier covers everything before)
-    if (k > 0) { const int last = (k - 1) % WIH_STAGES; mbar_wait(&bars[last], (phase_bits >> last) & 1u); }
-    cp_async_wait<0>();
+    __syncwarp();
+    // drain: the last item's UMMAs (commits are ordered, so its barrier covers everything before)
+    if (mine > 0) mbar_wait(fin, 0);
     tc_fence_after_sync();
     if (started) {
         const int row = tid & (TM - 1), half = tid >> 7;          // 2 column halves of 80
@@ -498,8 +492,8 @@ __global__ void __launch_bounds__(WIH_THREADS, 1) tc_wih_from_u_kernel(ItemArgs 
                 float v[8];
                 tmem_ld8(tmem_addr(tmem, lane_base, uint32_t(mb) * CP + n0), v);
                 if (ok) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) atomicAdd(a.ws.dwih + size_t(orow) * CP + n0 + e, v[e]);
+                    red_add_v4(a.ws.dwih + size_t(orow) * CP + n0, v[0], v[1], v[2], v[3]);
+                    red_add_v4(a.ws.dwih + size_t(orow) * CP + n0 + 4, v[4], v[5], v[6], v[7]);
                 }
             }
         }

@@ -348,3 +348,39 @@ def test_bf16_tc_heads_sweep_sections_vs_fp32_kernels(case, cuda_device):
     assert _cos(g16, g32) >= 0.999
     if case == "guard":   # the tripped head gets exact zeros (module.py:149-150)
         assert float(L.view(g16, "factor_predictor.attention_layers.3.query").abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["eval", "predict"])
+def test_bf16_tc_heads_forward_modes_vs_fp32_kernels(mode, cuda_device):
+    """Tensor-core heads forward (heads_tc.cu) in eval mode and through FactorVAE.prediction (decoder fed by the prior,
+    third tile loop) on ragged dates, against the fp32 CUDA-core kernels with the same injected eps."""
+    from factorvae_b200 import engine
+    import factorvae_b200 as fb
+    H, K, T = 20, 20, 4
+    torch.manual_seed(31)
+    m = fb.FactorVAE(fb.FeatureExtractor(158, H), fb.FactorEncoder(K, 128, H),
+                     fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, K)), fb.FactorPredictor(H, K))
+    L = engine.ParamLayout(158, H, K, 128)
+    flat = L.pack(m.state_dict(), cuda_device)
+    counts = [1, 130, 257, 64, 300]
+    ptr = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=cuda_device)
+    S = int(ptr[-1])
+    g = torch.Generator(device=cuda_device).manual_seed(8)
+    x = torch.randn(S, T, 158, device=cuda_device, generator=g).clamp_(-3, 3)
+    y = torch.randn(S, device=cuda_device, generator=g)
+    eps = torch.randn(S, device=cuda_device, generator=g)
+    predict = mode == "predict"
+    res = {}
+    for prec in ("fp32", "bf16"):
+        out, _ = engine.elbo_forward(L, flat, x, None if predict else y, ptr, eps=eps, train=False, precision=prec, predict=predict)
+        res[prec] = {k: v.clone() for k, v in out.items() if v is not None}
+    o32, o16 = res["fp32"], res["bf16"]
+    assert float((o16["mu_y"] - o32["mu_y"]).abs().max()) <= 1e-2 * max(1.0, float(o32["mu_y"].abs().max()))
+    assert _relmax(o16["sigma_y"], o32["sigma_y"]) <= 2e-2
+    assert float((o16["yhat"] - o32["yhat"]).abs().max()) <= 3e-2 * max(1.0, float(o32["yhat"].abs().max()))
+    assert float((o16["mu_prior"] - o32["mu_prior"]).abs().max()) <= 1e-2
+    assert _relmax(o16["sigma_prior"], o32["sigma_prior"]) <= 2e-2
+    if not predict:
+        assert float((o16["mu_post"] - o32["mu_post"]).abs().max()) <= 1e-2
+        assert _relmax(o16["sigma_post"], o32["sigma_post"]) <= 2e-2
+        assert abs(float(o16["loss"]) - float(o32["loss"])) <= 2e-2 * abs(float(o32["loss"]))
