@@ -132,14 +132,18 @@ __global__ void tc_prep_kernel(PrepArgs a) {
         put_img(a.ws.whhT, HP, k, col, v);
     }
     // biases ride in column C of the images (column C of the xhat / u operand tiles is the constant 1)
-    for (int n = tid; n < CP; n += nth) {
+    for (int w0 = tid; w0 < CP * 8; w0 += nth) {             // 8 threads per output (CP * 8 is a multiple of 32)
+        const int n = w0 >> 3, part = w0 & 7;
         float v = 0.f;
-        if (n < C) {
-            v = a.b1[n];
-            for (int k = 0; k < C; ++k) v = fmaf(a.W1[n * C + k], a.ln_b[k], v);
+        if (n < C)
+            for (int k = part; k < C; k += 8) v = fmaf(a.W1[n * C + k], a.ln_b[k], v);
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (part == 0) {
+            if (n < C) v += a.b1[n];
+            a.ws.b1f[n] = v;
+            put_img(a.ws.w1g, CP, n, C, v);
         }
-        a.ws.b1f[n] = v;
-        put_img(a.ws.w1g, CP, n, C, v);
     }
     for (int col = tid; col < NC; col += nth) {
         int gate, j;
@@ -504,15 +508,19 @@ __global__ void tc_post_kernel(PostArgs a) {
     }
     for (int o = tid; o < C; o += nth) atomicAdd(a.g.b1 + o, a.q[o * CP + C]);
     // dgamma[i] = sum_o W1[o][i] Q[o][i];  dbeta[i] = sum_o W1[o][i] db1[o]
-    for (int i = tid; i < C; i += nth) {
+    // 8 threads per column, spread over the grid: the column sums are latency-bound otherwise
+    for (int w0 = tid; w0 < ((C * 8 + 31) & ~31); w0 += nth) {
+        const int i = w0 >> 3, part = w0 & 7;
         float dg = 0.f, db = 0.f;
-        for (int o = 0; o < C; ++o) {
-            const float w = a.W1[o * C + i];
-            dg = fmaf(w, a.q[o * CP + i], dg);
-            db = fmaf(w, a.q[o * CP + C], db);
-        }
-        atomicAdd(a.g.ln_w + i, dg);
-        atomicAdd(a.g.ln_b + i, db);
+        if (i < C)
+            for (int o = part; o < C; o += 8) {
+                const float w = a.W1[o * C + i];
+                dg = fmaf(w, a.q[o * CP + i], dg);
+                db = fmaf(w, a.q[o * CP + C], db);
+            }
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) { dg += __shfl_xor_sync(0xffffffffu, dg, s); db += __shfl_xor_sync(0xffffffffu, db, s); }
+        if (i < C && part == 0) { atomicAdd(a.g.ln_w + i, dg); atomicAdd(a.g.ln_b + i, db); }
     }
     // dW_ih / db_ih: un-permute the gate rows
     for (int idx = tid; idx < 3 * H * (C + 1); idx += nth) {

@@ -62,18 +62,22 @@ struct Smem {
 // prep: collapse the K attention heads' key projections (date independent)
 // ------------------------------------------------------------------------------------------
 __global__ void heads_prep_kernel(HeadsArgs a, int zero_acc) {
+    __shared__ float sWk[kMaxH * kMaxH];     // one coalesced pass over W_k, then the products run out of shared memory
+    __shared__ float sq[kMaxH], sbk[kMaxH];
     const int k = blockIdx.x, H = a.H;
-    const float* q = a.w.q + size_t(k) * H;
     const float* Wk = a.w.Wk + size_t(k) * H * H;
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) sWk[i] = Wk[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { sq[i] = a.w.q[size_t(k) * H + i]; sbk[i] = a.w.bk[size_t(k) * H + i]; }
+    __syncthreads();
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
         float g = 0.f;
-        for (int hp = 0; hp < H; ++hp) g = fmaf(q[hp], Wk[hp * H + h], g);
+        for (int hp = 0; hp < H; ++hp) g = fmaf(sq[hp], sWk[hp * H + h], g);
         a.sv.G[k * H + h] = g;
         if (zero_acc) a.sv.dG[k * H + h] = 0.f;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == blockDim.x - 1) {
         float c = 0.f;
-        for (int h = 0; h < H; ++h) c = fmaf(q[h], a.w.bk[size_t(k) * H + h], c);
+        for (int h = 0; h < H; ++h) c = fmaf(sq[h], sbk[h], c);
         a.sv.cvec[k] = c;
         if (zero_acc) a.sv.dc[k] = 0.f;
     }
@@ -878,7 +882,7 @@ int set_smem(KernelT kernel, size_t bytes) {
 }  // namespace
 
 int heads_prep(const HeadsArgs& a, bool zero_grad_acc, cudaStream_t stream) {
-    heads_prep_kernel<<<a.K, 64, 0, stream>>>(a, zero_grad_acc ? 1 : 0); count_launch();
+    heads_prep_kernel<<<a.K, 128, 0, stream>>>(a, zero_grad_acc ? 1 : 0); count_launch();
     return int(cudaGetLastError());
 }
 
