@@ -167,10 +167,19 @@ struct GruArgs {
     int gi_ring;          // forward: stream the gate pre-activation tiles through a 2-stage bulk-copy ring in shared memory
 };
 
+// Threads: (row of the tile, group of BPT 8-unit blocks) -- 128 * NB8 / BPT threads per CTA.  A thread owns 8*BPT hidden
+// units of one row: their gate columns of the accumulator, their chunks of the GI tile and of the h operand tile.
+// Each CTA is one latency-bound chain (barrier -> UMMA -> gate math per time step), so throughput comes from resident
+// CTAs: small H runs thread-per-row (BPT = NB8, 4 CTAs/SM); large H splits the row (BPT = 1) to shorten the chain.
+__host__ __device__ constexpr int gru_bpt(int NB8) { return NB8 <= 3 ? NB8 : 1; }
+__host__ __device__ constexpr int gru_threads(int NB8) { return TM * (NB8 / gru_bpt(NB8)); }
+__host__ __device__ constexpr int gru_min_ctas(int NB8) { return NB8 <= 3 ? 4 : (NB8 == 4 ? 2 : 1); }
+
 template <int NB8, uint32_t TCOLS>
-__global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
+__global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_fwd_kernel(GruArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int NTHR = gru_threads(NB8), BPT = gru_bpt(NB8);
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), blk0 = (tid >> 7) * BPT;
     const int H = a.H, NC = a.NC, HP = a.HP, NCH = NC / 8, HCH = HP / 8;
     unsigned char* sWhh = smem;                                   // [HCH][NC][16]
     unsigned char* sH = sWhh + uint32_t(HCH) * NC * 16;           // [HCH][128][16]
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
     const uint32_t gi_bytes = uint32_t(NCH) * TILE_CH;            // one step's tile [NCH][128][16]
     const bool ring = a.gi_ring != 0;
     copy_image(sWhh, a.ws.whh, uint32_t(HCH) * NC * 16);
-    for (int i = tid; i < HP; i += TM) sBhn[i] = a.ws.bhn[i];
+    for (int i = tid; i < HP; i += NTHR) sBhn[i] = a.ws.bhn[i];
     if (tid == 0) { mbar_init(bar, 1); mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
     // flattened (tile, step) sequence of this CTA: q -> tile blockIdx.x + (q / T) * gridDim.x, step q % T
@@ -199,15 +208,15 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = uint32_t(warp) * 32u;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
     uint32_t phase = 0;
     if (ring && tid == 0) { if (total_q > 0) fill(0); if (total_q > 1) fill(1); }
     int64_t q = 0;
     for (int64_t st = blockIdx.x; st < a.NT; st += gridDim.x) {
-        float h[8 * NB8];
+        float h[8 * BPT];
 #pragma unroll
-        for (int j = 0; j < 8 * NB8; ++j) h[j] = 0.f;
-        const int64_t s = st * TM + tid;
+        for (int u = 0; u < 8 * BPT; ++u) h[u] = 0.f;
+        const int64_t s = st * TM + row;
         for (int t = 0; t < a.T; ++t, ++q) {
             if (t > 0) {
                 fence_async_smem();
@@ -222,17 +231,17 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
             // a CTA barrier (this step's, or the one that closed the previous tile) separates everybody's reads of
             // step q-1's stage from its refill with step q+1
             if (ring && tid == 0 && q >= 1 && q + 1 < total_q) fill(q + 1);
-            // my row's gate pre-activations of this step
-            uint4 gq[3 * NB8];
+            // my chunks (r | z | n per 8-unit block) of this step's gate pre-activations
+            uint4 gq[3 * BPT];
             if (ring) {
                 mbar_wait(&full[q & 1], uint32_t(q >> 1) & 1u);
                 const unsigned char* gin = sGi + (q & 1) * gi_bytes;
 #pragma unroll
-                for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, c));
+                for (int c = 0; c < 3 * BPT; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, row, 3 * blk0 + c));
             } else {                                              // direct global loads, in flight while the MMA runs
                 const unsigned char* gin = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
 #pragma unroll
-                for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, tid, c));
+                for (int c = 0; c < 3 * BPT; ++c) gq[c] = *reinterpret_cast<const uint4*>(gin + tile_off(TM, row, 3 * blk0 + c));
             }
             if (t > 0) {
                 mbar_wait(bar, phase);
@@ -241,48 +250,51 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
             }
             unsigned char* hout = reinterpret_cast<unsigned char*>(a.ws.hall) + size_t(st * a.T + t) * HCH * TILE_CH;
 #pragma unroll
-            for (int b = 0; b < NB8; ++b) {
+            for (int bb = 0; bb < BPT; ++bb) {
+                const int blk = blk0 + bb;
                 float ghr[8], ghz[8], ghn[8], gir[8], giz[8], gin8[8];
                 if (t > 0) {
-                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24), ghr);
-                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 8), ghz);
-                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 16), ghn);
+                    tmem_ld8(tmem_addr(tmem, lane_base, blk * 24), ghr);
+                    tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 8), ghz);
+                    tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 16), ghn);
                 } else {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) ghr[u] = ghz[u] = ghn[u] = 0.f;
                 }
-                unpack8(gq[3 * b], gir);
-                unpack8(gq[3 * b + 1], giz);
-                unpack8(gq[3 * b + 2], gin8);
+                unpack8(gq[3 * bb], gir);
+                unpack8(gq[3 * bb + 1], giz);
+                unpack8(gq[3 * bb + 2], gin8);
                 float hv[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int j = b * 8 + u;
+                    const int j = blk * 8 + u;
                     const float r = sigmoid_fast(gir[u] + ghr[u]);
                     const float z = sigmoid_fast(giz[u] + ghz[u]);
                     const float n = tanh_fast(gin8[u] + r * (ghn[u] + sBhn[j]));
-                    float hn = fmaf(z, h[j] - n, n);            // (1-z) n + z h
+                    float hn = fmaf(z, h[bb * 8 + u] - n, n);   // (1-z) n + z h
                     if (j >= H) hn = 0.f;
-                    h[j] = hn;
+                    h[bb * 8 + u] = hn;
                     hv[u] = (j == H) ? 1.f : hn;                 // the ones column of the operand tile
                 }
                 const uint4 pk = make_uint4(pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]), pack_bf16(hv[4], hv[5]), pack_bf16(hv[6], hv[7]));
-                *reinterpret_cast<uint4*>(sH + tile_off(TM, tid, b)) = pk;
-                *reinterpret_cast<uint4*>(hout + tile_off(TM, tid, b)) = pk;
+                *reinterpret_cast<uint4*>(sH + tile_off(TM, row, blk)) = pk;
+                *reinterpret_cast<uint4*>(hout + tile_off(TM, row, blk)) = pk;
             }
-            for (int b = NB8; b < HCH; ++b) {                    // padding chunks (hold the ones column when H % 8 == 0)
-                const uint32_t one = (H >= b * 8 && H < b * 8 + 8) ? (0x3F80u << (16 * (H & 1))) : 0u;
-                uint4 pk = make_uint4(0, 0, 0, 0);
-                const int w = (H - b * 8) >> 1;
-                if (one) { if (w == 0) pk.x = one; else if (w == 1) pk.y = one; else if (w == 2) pk.z = one; else pk.w = one; }
-                *reinterpret_cast<uint4*>(sH + tile_off(TM, tid, b)) = pk;
-                *reinterpret_cast<uint4*>(hout + tile_off(TM, tid, b)) = pk;
+            if (blk0 == 0) {
+                for (int b = NB8; b < HCH; ++b) {                // padding chunks (hold the ones column when H % 8 == 0)
+                    const uint32_t one = (H >= b * 8 && H < b * 8 + 8) ? (0x3F80u << (16 * (H & 1))) : 0u;
+                    uint4 pk = make_uint4(0, 0, 0, 0);
+                    const int w = (H - b * 8) >> 1;
+                    if (one) { if (w == 0) pk.x = one; else if (w == 1) pk.y = one; else if (w == 2) pk.z = one; else pk.w = one; }
+                    *reinterpret_cast<uint4*>(sH + tile_off(TM, row, b)) = pk;
+                    *reinterpret_cast<uint4*>(hout + tile_off(TM, row, b)) = pk;
+                }
             }
             tc_fence_before_sync();
         }
         if (s < a.S) {
 #pragma unroll
-            for (int j = 0; j < 8 * NB8; ++j) if (j < H) a.e[s * H + j] = h[j];
+            for (int u = 0; u < 8 * BPT; ++u) { const int j = blk0 * 8 + u; if (j < H) a.e[s * H + j] = h[u]; }
         }
         __syncthreads();      // sH is rewritten by the next tile's first step only after everyone is done
     }
@@ -293,9 +305,10 @@ __global__ void __launch_bounds__(TM) tc_gru_fwd_kernel(GruArgs a) {
 
 // ---- K3: GRU backward (BPTT) -------------------------------------------------------------------------------------
 template <int NB8, uint32_t TCOLS>
-__global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
+__global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bwd_kernel(GruArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int NTHR = gru_threads(NB8), BPT = gru_bpt(NB8), NTB = NB8 / BPT;
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), tblk = tid >> 7, blk0 = tblk * BPT;   // thread = (row, BPT blocks)
     const int H = a.H, NC = a.NC, HP = a.HP, NCH = NC / 8, HCH = HP / 8;
     const int MB = NC > 128 ? 2 : 1;                              // M blocks of the dW_hh accumulator
     unsigned char* sWhh = smem;                                   // [HCH][NC][16]   B of gh = h W_hh^T
@@ -309,8 +322,8 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
     const uint32_t COL_DH = 0u, COL_DW = uint32_t(NC);
     copy_image(sWhh, a.ws.whh, uint32_t(HCH) * NC * 16);
     copy_image(sWhhT, a.ws.whhT, uint32_t(NCH) * HP * 16);
-    for (uint32_t i = tid; i < uint32_t(16 * MB) * TILE_CH / 16; i += TM) reinterpret_cast<uint4*>(sDgh)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < HP; i += TM) sBhn[i] = a.ws.bhn[i];
+    for (uint32_t i = tid; i < uint32_t(16 * MB) * TILE_CH / 16; i += NTHR) reinterpret_cast<uint4*>(sDgh)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < HP; i += NTHR) sBhn[i] = a.ws.bhn[i];
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
     fence_async_smem();
@@ -318,46 +331,48 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = uint32_t(warp) * 32u;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
     uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
     bool dw_pending = false, dw_started = false;
+    // constant chunk of the h operand tile: zeros, with the ones column where H falls into chunk b
+    auto const_chunk = [&](int b) {
+        uint4 pk = make_uint4(0, 0, 0, 0);
+        if (H >= b * 8 && H < b * 8 + 8) {
+            const uint32_t one = 0x3F80u << (16 * (H & 1));
+            const int w = (H - b * 8) >> 1;
+            if (w == 0) pk.x = one; else if (w == 1) pk.y = one; else if (w == 2) pk.z = one; else pk.w = one;
+        }
+        return pk;
+    };
     for (int64_t st = blockIdx.x; st < a.NT; st += gridDim.x) {
-        float dh[8 * NB8];
-        constexpr int MAXHCH = NB8 + 2;          // HP/8 <= NB8 + 2
-        uint4 hq[MAXHCH];
-        const int64_t s = st * TM + tid;
+        float dh[8 * BPT];
+        uint4 hq[BPT];                           // my chunks of h_{t-1}, prefetched one step ahead
+        const int64_t s = st * TM + row;
 #pragma unroll
-        for (int j = 0; j < 8 * NB8; ++j) dh[j] = (s < a.S && j < H) ? a.dE[s * H + j] : 0.f;
-        // my row's gate pre-activations: step T-1 here, step t-1 right after step t's gate epilogue (its registers are
-        // free by then), so the load latency hides behind the dh GEMM and the next step's gh GEMM
-        uint4 gq[3 * NB8];
+        for (int u = 0; u < 8 * BPT; ++u) { const int j = blk0 * 8 + u; dh[u] = (s < a.S && j < H) ? a.dE[s * H + j] : 0.f; }
+        // my chunks of the gate pre-activations: step T-1 here, step t-1 right after step t's gate epilogue
+        uint4 gq[3 * BPT];
         {
             const unsigned char* g0 = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(st * a.T + a.T - 1) * NCH * TILE_CH;
 #pragma unroll
-            for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(g0 + tile_off(TM, tid, c));
+            for (int c = 0; c < 3 * BPT; ++c) gq[c] = *reinterpret_cast<const uint4*>(g0 + tile_off(TM, row, 3 * blk0 + c));
         }
         for (int t = a.T - 1; t >= 0; --t) {
             if (dw_pending) { mbar_wait(&bars[2], ph2); ph2 ^= 1; dw_pending = false; }   // sHp / sDgh are free again
-            // h_{t-1} operand tile (my row of it was prefetched into registers during the previous step)
+            // h_{t-1} operand tile
             if (t > 0) {
                 if (t == a.T - 1) {
                     const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 1) * HCH * TILE_CH;
 #pragma unroll
-                    for (int b = 0; b < MAXHCH; ++b) if (b < HCH) hq[b] = *reinterpret_cast<const uint4*>(hin + tile_off(TM, tid, b));
+                    for (int bb = 0; bb < BPT; ++bb) hq[bb] = *reinterpret_cast<const uint4*>(hin + tile_off(TM, row, blk0 + bb));
                 }
-#pragma unroll
-                for (int b = 0; b < MAXHCH; ++b) if (b < HCH) *reinterpret_cast<uint4*>(sHp + tile_off(TM, tid, b)) = hq[b];
             } else {
-                for (int b = 0; b < HCH; ++b) {
-                    uint4 pk = make_uint4(0, 0, 0, 0);
-                    if (H >= b * 8 && H < b * 8 + 8) {
-                        const uint32_t one = 0x3F80u << (16 * (H & 1));
-                        const int w = (H - b * 8) >> 1;
-                        if (w == 0) pk.x = one; else if (w == 1) pk.y = one; else if (w == 2) pk.z = one; else pk.w = one;
-                    }
-                    *reinterpret_cast<uint4*>(sHp + tile_off(TM, tid, b)) = pk;
-                }
+#pragma unroll
+                for (int bb = 0; bb < BPT; ++bb) hq[bb] = const_chunk(blk0 + bb);
             }
+#pragma unroll
+            for (int bb = 0; bb < BPT; ++bb) *reinterpret_cast<uint4*>(sHp + tile_off(TM, row, blk0 + bb)) = hq[bb];
+            if (blk0 == 0) for (int b = NB8; b < HCH; ++b) *reinterpret_cast<uint4*>(sHp + tile_off(TM, row, b)) = const_chunk(b);
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -366,12 +381,14 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
                 issue_row_gemm(tmem, 0, smem_u32(sHp), smem_u32(sWhh), NC, NC, HP / 16);
                 mma_commit(&bars[0]);
             }
-            // global loads in flight while the MMA runs: next step's h_{t-2}
             unsigned char* gio = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
-            if (t > 1) {
+            uint4 hcur[BPT];                     // h_{t-1}, my chunks
+#pragma unroll
+            for (int bb = 0; bb < BPT; ++bb) hcur[bb] = hq[bb];
+            if (t > 1) {                         // next step's h_{t-2}, in flight while the MMA runs
                 const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 2) * HCH * TILE_CH;
 #pragma unroll
-                for (int b = 0; b < MAXHCH; ++b) if (b < HCH) hq[b] = *reinterpret_cast<const uint4*>(hin + tile_off(TM, tid, b));
+                for (int bb = 0; bb < BPT; ++bb) hq[bb] = *reinterpret_cast<const uint4*>(hin + tile_off(TM, row, blk0 + bb));
             }
             if (t > 0) {
                 mbar_wait(&bars[0], ph0);
@@ -379,53 +396,54 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
                 tc_fence_after_sync();
             }
 #pragma unroll
-            for (int b = 0; b < NB8; ++b) {
+            for (int bb = 0; bb < BPT; ++bb) {
+                const int blk = blk0 + bb;
                 float ghr[8], ghz[8], ghn[8], gir[8], giz[8], gin8[8], hp[8];
                 if (t > 0) {
-                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24), ghr);
-                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 8), ghz);
-                    tmem_ld8(tmem_addr(tmem, lane_base, b * 24 + 16), ghn);
+                    tmem_ld8(tmem_addr(tmem, lane_base, blk * 24), ghr);
+                    tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 8), ghz);
+                    tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 16), ghn);
                 } else {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) ghr[u] = ghz[u] = ghn[u] = 0.f;
                 }
-                unpack8(gq[3 * b], gir);
-                unpack8(gq[3 * b + 1], giz);
-                unpack8(gq[3 * b + 2], gin8);
-                unpack8(*reinterpret_cast<const uint4*>(sHp + tile_off(TM, tid, b)), hp);
+                unpack8(gq[3 * bb], gir);
+                unpack8(gq[3 * bb + 1], giz);
+                unpack8(gq[3 * bb + 2], gin8);
+                unpack8(hcur[bb], hp);
                 float dar[8], daz[8], dan[8], dnr[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int j = b * 8 + u;
+                    const int j = blk * 8 + u;
                     const float r = sigmoid_fast(gir[u] + ghr[u]);
                     const float z = sigmoid_fast(giz[u] + ghz[u]);
                     const float hn = ghn[u] + sBhn[j];
                     const float n = tanh_fast(gin8[u] + r * hn);
                     const float hprev = (j < H) ? hp[u] : 0.f;
-                    const float d = dh[j];
+                    const float d = dh[bb * 8 + u];
                     const float dn = d * (1.f - z);
                     const float dz = d * (hprev - n);
                     dan[u] = dn * (1.f - n * n);
                     dar[u] = dan[u] * hn * r * (1.f - r);
                     daz[u] = dz * z * (1.f - z);
                     dnr[u] = dan[u] * r;
-                    dh[j] = d * z;
+                    dh[bb * 8 + u] = d * z;
                 }
                 const uint4 pr = make_uint4(pack_bf16(dar[0], dar[1]), pack_bf16(dar[2], dar[3]), pack_bf16(dar[4], dar[5]), pack_bf16(dar[6], dar[7]));
                 const uint4 pz = make_uint4(pack_bf16(daz[0], daz[1]), pack_bf16(daz[2], daz[3]), pack_bf16(daz[4], daz[5]), pack_bf16(daz[6], daz[7]));
                 const uint4 pn = make_uint4(pack_bf16(dan[0], dan[1]), pack_bf16(dan[2], dan[3]), pack_bf16(dan[4], dan[5]), pack_bf16(dan[6], dan[7]));
                 const uint4 pq = make_uint4(pack_bf16(dnr[0], dnr[1]), pack_bf16(dnr[2], dnr[3]), pack_bf16(dnr[4], dnr[5]), pack_bf16(dnr[6], dnr[7]));
-                *reinterpret_cast<uint4*>(gio + tile_off(TM, tid, 3 * b)) = pr;          // d gi, in place
-                *reinterpret_cast<uint4*>(gio + tile_off(TM, tid, 3 * b + 1)) = pz;
-                *reinterpret_cast<uint4*>(gio + tile_off(TM, tid, 3 * b + 2)) = pn;
-                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b)) = pr;         // d gh operand tile
-                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b + 1)) = pz;
-                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, tid, 3 * b + 2)) = pq;
+                *reinterpret_cast<uint4*>(gio + tile_off(TM, row, 3 * blk)) = pr;          // d gi, in place
+                *reinterpret_cast<uint4*>(gio + tile_off(TM, row, 3 * blk + 1)) = pz;
+                *reinterpret_cast<uint4*>(gio + tile_off(TM, row, 3 * blk + 2)) = pn;
+                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, row, 3 * blk)) = pr;         // d gh operand tile
+                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, row, 3 * blk + 1)) = pz;
+                *reinterpret_cast<uint4*>(sDgh + tile_off(TM, row, 3 * blk + 2)) = pq;
             }
             if (t > 0) {
                 const unsigned char* gn = gio - size_t(NCH) * TILE_CH;          // step t-1 of this tile
 #pragma unroll
-                for (int c = 0; c < 3 * NB8; ++c) gq[c] = *reinterpret_cast<const uint4*>(gn + tile_off(TM, tid, c));
+                for (int c = 0; c < 3 * BPT; ++c) gq[c] = *reinterpret_cast<const uint4*>(gn + tile_off(TM, row, 3 * blk0 + c));
             }
             fence_async_smem();
             tc_fence_before_sync();
@@ -444,24 +462,25 @@ __global__ void __launch_bounds__(TM) tc_gru_bwd_kernel(GruArgs a) {
             ph1 ^= 1;
             tc_fence_after_sync();
 #pragma unroll
-            for (int b = 0; b < NB8; ++b) {
+            for (int bb = 0; bb < BPT; ++bb) {
                 float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, COL_DH + b * 8), v);
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_DH + (blk0 + bb) * 8), v);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) dh[b * 8 + u] += v[u];
+                for (int u = 0; u < 8; ++u) dh[bb * 8 + u] += v[u];
             }
             tc_fence_before_sync();
         }
     }
     if (dw_pending) { mbar_wait(&bars[2], ph2); }
     tc_fence_after_sync();
-    // flush dW_hh / db_hh: lane = permuted gate row, columns = hidden index (column H = bias)
+    // flush dW_hh / db_hh: lane = permuted gate row, columns = hidden index (column H = bias); the 8-column chunks are
+    // dealt round-robin to the thread blocks
     if (dw_started) {
         for (int mb = 0; mb < MB; ++mb) {
-            const int col = mb * 128 + tid;
+            const int col = mb * 128 + row;
             int gate, j;
             const bool ok = col < NC && unperm_col(col, H, gate, j);
-            for (int c8 = 0; c8 < HCH; ++c8) {
+            for (int c8 = tblk; c8 < HCH; c8 += NTB) {
                 float v[8];
                 tmem_ld8(tmem_addr(tmem, lane_base, COL_DW + mb * HP + c8 * 8), v);
                 if (ok) {
@@ -551,11 +570,26 @@ int launch_smem(KernelT k, int grid, size_t smem, cudaStream_t st, const ItemArg
     return int(cudaGetLastError());
 }
 template <typename KernelT>
-int launch_gru(KernelT k, int grid, size_t smem, cudaStream_t st, const GruArgs& a) {
+int launch_gru(KernelT k, int threads, uint32_t tmem_cols, size_t smem, cudaStream_t st, const GruArgs& a) {
     if (smem > 227 * 1024) return FVAE_ERR_LIMIT;
     cudaError_t ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (ce != cudaSuccess) return int(ce);
-    k<<<grid, TM, smem, st>>>(a); count_launch();
+    // resident CTAs per SM, from the hardware limits the kernel touches: threads, registers (allocated per warp in units
+    // of 256), shared memory (+1 KB reserved per CTA), TMEM columns
+    cudaFuncAttributes fa;
+    if ((ce = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return int(ce);
+    const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+    int occ = 2048 / threads;
+    const int by_regs = 65536 / (regs_per_warp * (threads / 32));
+    const int by_smem = int(size_t(227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+    const int by_tmem = int(512u / tmem_cols);
+    if (occ > by_regs) occ = by_regs;
+    if (occ > by_smem) occ = by_smem;
+    if (occ > by_tmem) occ = by_tmem;
+    if (occ < 1) occ = 1;
+    const int64_t slots = int64_t(num_sms()) * occ;
+    const int grid = int(a.NT < slots ? a.NT : slots);
+    k<<<grid, threads, smem, st>>>(a); count_launch();
     return int(cudaGetLastError());
 }
 
@@ -622,10 +656,8 @@ int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, 
         const size_t with_ring = smem + 256 + 2 * size_t(NC / 8) * TILE_CH;
         if (NC <= 128 && with_ring <= 56 * 1024) { g.gi_ring = 1; smem = with_ring; }
     }
-    const int ctas_per_sm = NC <= 128 ? 4 : 2;
-    const int grid = int(a.NT < int64_t(nsm) * ctas_per_sm ? a.NT : int64_t(nsm) * ctas_per_sm);
-    if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 128>, grid, smem, st, g)); }
-    else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 256>, grid, smem, st, g)); }
+    if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 128>, gru_threads(kNB), 128, smem, st, g)); }
+    else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 256>, gru_threads(kNB), 256, smem, st, g)); }
     return rc;
 }
 
@@ -640,12 +672,9 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         const int MB = NC > 128 ? 2 : 1;
         const size_t smem = size_t(HP / 8) * NC * 16 + size_t(NC / 8) * HP * 16 + size_t(HP / 8) * TILE_CH + size_t(16 * MB) * TILE_CH + HP * 4 + 64;
         const uint32_t cols = uint32_t(NC + MB * HP);
-        int ctas_per_sm = cols <= 128 ? 4 : (cols <= 256 ? 2 : 1);
-        while (ctas_per_sm > 1 && smem * ctas_per_sm > kMaxSmem) ctas_per_sm >>= 1;
-        const int grid = int(a.NT < int64_t(nsm) * ctas_per_sm ? a.NT : int64_t(nsm) * ctas_per_sm);
-        if (cols <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 128>, grid, smem, st, g)); }
-        else if (cols <= 256) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 256>, grid, smem, st, g)); }
-        else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 512>, grid, smem, st, g)); }
+        if (cols <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 128>, gru_threads(kNB), 128, smem, st, g)); }
+        else if (cols <= 256) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 256>, gru_threads(kNB), 256, smem, st, g)); }
+        else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 512>, gru_threads(kNB), 512, smem, st, g)); }
         if (rc != 0) return rc;
     }
     cudaError_t ce = cudaMemsetAsync(ws.q, 0, size_t(256) * CP * 4, st);
