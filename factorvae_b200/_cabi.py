@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libfvae_b200.so")
 F32, BF16 = 0, 1
 PREC_FP32, PREC_BF16_TC = 0, 1
 FLAG_TRAIN, FLAG_PHILOX = 1, 2
+FILL_NONE, FILL_FFILL, FILL_FFILL_BFILL = 0, 1, 2
+ABI_VERSION = 2
 
 SECTIONS = [
     "LN_W", "LN_B", "W1", "B1", "WIH", "WHH", "BIH", "BHH",
@@ -27,7 +29,9 @@ class Shape(C.Structure):
 
 
 class Panel(C.Structure):
-    _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("seq_pitch", C.c_int64), ("row_pitch", C.c_int64)]
+    # row_index / num_rows: resident-panel form (NULL / 0 for dense windows), see include/fvae_b200.h
+    _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("seq_pitch", C.c_int64), ("row_pitch", C.c_int64),
+                ("row_index", C.c_void_p), ("num_rows", C.c_int64)]
 
 
 class Noise(C.Structure):
@@ -81,7 +85,11 @@ def lib() -> C.CDLL:
     L.fvae_debug_front_forward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i64, vp]
     L.fvae_workspace_latent.restype = vp
     L.fvae_workspace_latent.argtypes = [C.POINTER(Shape), i32, vp]
-    if L.fvae_abi_version() != 1:
+    L.fvae_window_index.restype = C.c_int
+    L.fvae_window_index.argtypes = [vp, i32, i32, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]
+    L.fvae_gather_windows.restype = C.c_int
+    L.fvae_gather_windows.argtypes = [C.POINTER(Panel), i64, i32, i32, vp, i32, vp]
+    if L.fvae_abi_version() != ABI_VERSION:
         raise ImportError("libfvae_b200.so has an unexpected ABI version")
     _lib = L
     return L
@@ -89,7 +97,7 @@ def lib() -> C.CDLL:
 
 EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_debug_front_forward", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
            "fvae_elbo_forward", "fvae_elbo_backward", "fvae_predict", "fvae_fe_forward", "fvae_fe_backward",
-           "fvae_workspace_latent"]
+           "fvae_workspace_latent", "fvae_window_index", "fvae_gather_windows"]
 
 
 class FvaeError(RuntimeError):

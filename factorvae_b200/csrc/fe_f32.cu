@@ -40,13 +40,13 @@ WsF32 carve_f32(const FeDims& d, void* base) {
 
 // ---- LayerNorm over the C features of each (sequence, time) row: one warp per row ------------
 template <typename XT>
-__global__ void ln_rows_kernel(const XT* __restrict__ x, int64_t seq_pitch, int64_t row_pitch, int T, int C,
-                               int64_t row0, int nrows, const float* __restrict__ gamma,
+__global__ void ln_rows_kernel(const XT* __restrict__ x, int64_t seq_pitch, int64_t row_pitch, const int32_t* __restrict__ row_index,
+                               int T, int C, int64_t row0, int nrows, const float* __restrict__ gamma,
                                const float* __restrict__ beta, float* __restrict__ xn, float* __restrict__ xhat) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nrows) return;
     const int64_t row = row0 + warp;
-    const XT* src = x + (row / T) * seq_pitch + (row % T) * row_pitch;
+    const XT* src = row_index ? x + int64_t(row_index[row]) * row_pitch : x + (row / T) * seq_pitch + (row % T) * row_pitch;
     float v[kMaxC / 32];
     float sum = 0.f;
 #pragma unroll
@@ -333,7 +333,7 @@ void launch_ln(const fvae_panel& x, const FeDims& d, int64_t row0, int nrows, co
                cudaStream_t st) {
     const int warps_per_cta = 8;
     ln_rows_kernel<XT><<<grid_rows(nrows, warps_per_cta), 32 * warps_per_cta, 0, st>>>(
-        static_cast<const XT*>(x.data), x.seq_pitch, x.row_pitch, d.T, d.C, row0, nrows, w.ln_w, w.ln_b, xn, xhat); count_launch();
+        static_cast<const XT*>(x.data), x.seq_pitch, x.row_pitch, x.row_index, d.T, d.C, row0, nrows, w.ln_w, w.ln_b, xn, xhat); count_launch();
 }
 
 void run_ln(const fvae_panel& x, const FeDims& d, int64_t row0, int nrows, const FeW& w, float* xn, float* xhat,

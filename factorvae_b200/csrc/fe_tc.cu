@@ -595,7 +595,7 @@ int launch_gru(KernelT k, int threads, uint32_t tmem_cols, size_t smem, cudaStre
 
 ItemArgs make_item_args(const FeDims& d, const fvae_panel& x, const TcWs& ws) {
     ItemArgs a;
-    a.x = x.data; a.seq_pitch = x.seq_pitch; a.row_pitch = x.row_pitch;
+    a.x = x.data; a.seq_pitch = x.seq_pitch; a.row_pitch = x.row_pitch; a.row_index = x.row_index; a.num_rows = x.num_rows;
     a.S = d.S; a.T = d.T; a.C = d.C; a.H = d.H; a.NC = nc_of(d.H); a.HP = hp_of(d.H);
     a.NT = (int64_t(d.S) + TM - 1) / TM;
     a.prefetch = 0;

@@ -11,6 +11,7 @@
 
 struct ItemArgs {
     const void* x; int64_t seq_pitch, row_pitch;
+    const int32_t* row_index; int64_t num_rows;       // resident panel (NULL: dense windows)
     int S, T, C, H, NC, HP; int64_t NT;
     int prefetch;            // 1: dedicated raw-row stage, next item's rows are fetched during this item's MMAs
     TcWs ws;
@@ -60,7 +61,14 @@ __device__ __forceinline__ uint32_t slot_bytes(int C) {
 }
 template <typename XT>
 __device__ __forceinline__ const unsigned char* row_ptr(const ItemArgs& a, int64_t s, int t) {
+    if (a.row_index) return reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + int64_t(a.row_index[s * a.T + t]) * a.row_pitch);
     return reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + s * a.seq_pitch + int64_t(t) * a.row_pitch);
+}
+// one past the last byte of the panel allocation a 16-byte window may touch
+template <typename XT>
+__device__ __forceinline__ const unsigned char* panel_end(const ItemArgs& a) {
+    if (a.row_index) return reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + (a.num_rows - 1) * a.row_pitch + a.C);
+    return reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + int64_t(a.S - 1) * a.seq_pitch + int64_t(a.T - 1) * a.row_pitch + a.C);
 }
 template <typename XT>
 struct Rows { static constexpr int PER_PASS = sizeof(XT) == 2 ? TM : TM / 2; };
@@ -75,7 +83,7 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
     const int npieces = int(slot / 16);
     constexpr int NW = NTH / 32;
     const int64_t s0 = st * TM + r0;
-    if (s0 + Rows<XT>::PER_PASS + 1 <= a.S && npieces <= 64) {
+    if (!a.row_index && s0 + Rows<XT>::PER_PASS + 1 <= a.S && npieces <= 64) {
         const unsigned char* src = row_ptr<XT>(a, s0 + warp, t);
         const int64_t step = a.seq_pitch * int64_t(sizeof(XT)) * NW;
         uint32_t dst = smem_u32(stage) + uint32_t(warp) * slot + uint32_t(lane) * 16u;
@@ -89,7 +97,34 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
         }
         return;
     }
-    const unsigned char* x_end = row_ptr<XT>(a, a.S - 1, a.T - 1) + size_t(C) * sizeof(XT);
+    const unsigned char* x_end = panel_end<XT>(a);
+    if (a.row_index) {
+        // resident panel: lane k of the warp fetches the table row of the warp's k-th sequence, one shuffle per row after
+        constexpr int RPW = Rows<XT>::PER_PASS / NW;
+        int32_t myidx = -1;
+        {
+            const int64_t s = s0 + warp + int64_t(lane) * NW;
+            if (lane < RPW && s < a.S) myidx = a.row_index[s * a.T + t];
+        }
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+            const int32_t idx = __shfl_sync(0xffffffffu, myidx, k);
+            unsigned char* dst = stage + size_t(warp + k * NW) * slot;
+            if (idx >= 0) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + int64_t(idx) * a.row_pitch);
+                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
+                if (a0 + slot <= x_end) {
+                    for (int pc = lane; pc < npieces; pc += 32) cp_async16(smem_u32(dst + pc * 16), a0 + pc * 16);
+                } else {
+                    XT* d2 = reinterpret_cast<XT*>(dst + (src - a0));
+                    for (int c = lane; c < C; c += 32) d2[c] = reinterpret_cast<const XT*>(src)[c];
+                }
+            } else {
+                for (int pc = lane; pc < npieces; pc += 32) *reinterpret_cast<uint4*>(dst + pc * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        return;
+    }
     for (int rr = warp; rr < Rows<XT>::PER_PASS; rr += NW) {
         unsigned char* dst = stage + size_t(rr) * slot;
         const int64_t s = s0 + rr;

@@ -81,6 +81,10 @@ int check_shape(const fvae_shape* s, int precision) {
 int check_panel(const fvae_panel* x, const fvae_shape* s) {
     if (!x || !x->data) return FVAE_ERR_NULL;
     if (x->dtype != FVAE_F32 && x->dtype != FVAE_BF16) return FVAE_ERR_DTYPE;
+    if (x->row_index) {                                      // resident panel: rows named by the index
+        if (x->row_pitch < s->C || x->num_rows <= 0) return FVAE_ERR_SHAPE;
+        return FVAE_OK;
+    }
     if (x->row_pitch < s->C || x->seq_pitch < int64_t(s->T - 1) * x->row_pitch + s->C) return FVAE_ERR_SHAPE;
     return FVAE_OK;
 }

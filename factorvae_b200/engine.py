@@ -102,14 +102,49 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
                            f"(got device {t.device}).")
 
 
-def _panel(x: torch.Tensor) -> "_cabi.Panel":
+class IndexedWindows:
+    """The look-back windows in resident-panel form (include/fvae_b200.h, fvae_panel.row_index): `table` is the
+    (date, instrument) row table (R, pitch >= C) fp32|bf16 on the device, `row_index` (S, T) int32 names the table row of
+    every (sequence, time step).  Accepted wherever the engine takes the dense x (S, T, C); the kernels read the rows in
+    place, the T-fold duplicated window tensor of the reference's DataLoader is never built."""
+
+    def __init__(self, table: torch.Tensor, row_index: torch.Tensor, C_: int):
+        if table.dim() != 2 or table.stride(1) != 1 or table.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("table must be a (rows, pitch) fp32 / bf16 matrix with unit inner stride")
+        if row_index.dim() != 2 or row_index.dtype != torch.int32 or not row_index.is_contiguous():
+            raise ValueError("row_index must be a contiguous (S, T) int32 tensor")
+        if C_ > table.shape[1]:
+            raise ValueError("C exceeds the table width")
+        self.table, self.row_index, self.C = table, row_index, int(C_)
+
+    @property
+    def shape(self):
+        return (self.row_index.shape[0], self.row_index.shape[1], self.C)
+
+    @property
+    def is_cuda(self):
+        return self.table.is_cuda and self.row_index.is_cuda
+
+    @property
+    def device(self):
+        return self.table.device
+
+    @property
+    def dtype(self):
+        return self.table.dtype
+
+
+def _panel(x) -> "_cabi.Panel":
+    if isinstance(x, IndexedWindows):
+        return x, _cabi.Panel(x.table.data_ptr(), _cabi.F32 if x.table.dtype == torch.float32 else _cabi.BF16, 0,
+                              x.table.stride(0), x.row_index.data_ptr(), x.table.shape[0])
     if x.dim() != 3:
         raise ValueError("x must be (S, T, C)")
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.float()
     if x.stride(2) != 1:
         x = x.contiguous()
-    return x, _cabi.Panel(x.data_ptr(), _cabi.F32 if x.dtype == torch.float32 else _cabi.BF16, x.stride(0), x.stride(1))
+    return x, _cabi.Panel(x.data_ptr(), _cabi.F32 if x.dtype == torch.float32 else _cabi.BF16, x.stride(0), x.stride(1), None, 0)
 
 
 def tc_supported(C_: int, H: int) -> bool:

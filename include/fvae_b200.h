@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FVAE_ABI_VERSION 1
+#define FVAE_ABI_VERSION 2
 
 /* status codes (<0: argument errors) */
 #define FVAE_OK 0
@@ -71,12 +71,19 @@ typedef struct fvae_shape {
 } fvae_shape;
 
 /* the feature panel x[S][T][C]; innermost stride is 1.  The reference's CPU path feeds a
- * non-contiguous view with row pitch 159 (train_model.py:18): pitches are explicit.       */
+ * non-contiguous view with row pitch 159 (train_model.py:18): pitches are explicit.
+ * Resident-panel form (replaces the per-sample window gather of dataset.py:139-181): `data` is
+ * the (date, instrument) row table [num_rows][row_pitch] kept on the device once, and
+ * `row_index[s*T + t]` names the table row that is time step t of sequence s (what
+ * TSDataSampler._get_indices returns after ffill+bfill; missing -> the all-NaN sentinel row).
+ * The windows are then never materialised: the kernels read the T rows of a sequence in place. */
 typedef struct fvae_panel {
     const void* data;
     int32_t dtype;        /* FVAE_F32 | FVAE_BF16 */
-    int64_t seq_pitch;    /* elements between consecutive sequences */
+    int64_t seq_pitch;    /* elements between consecutive sequences (ignored with row_index) */
     int64_t row_pitch;    /* elements between consecutive time rows  */
+    const int32_t* row_index;  /* NULL: dense windows.  Else [S][T] row numbers into `data` (0 <= r < num_rows) */
+    int64_t num_rows;          /* rows of the table when row_index is given                                     */
 } fvae_panel;
 
 /* random inputs of the step.  Either explicit tensors (parity mode) or a Philox key. */
@@ -156,6 +163,26 @@ int fvae_debug_front_forward(const fvae_shape* shape, const fvae_panel* x, void*
 
 /* device e[S][H] of the last forward on this workspace (for tests / diagnostics). */
 const float* fvae_workspace_latent(const fvae_shape* shape, int32_t precision, const void* workspace);
+
+/* ---- resident panel: window index + gather (replaces dataset.py:139-181 TSDataSampler._get_indices /
+ *      __getitem__ and the label slice of train_model.py:17-22) ---------------------------------------
+ * idx_mat [D][I]: row number of (date d, instrument j) in the row table, -1 where the instrument has
+ * no row that date (TSDataSampler.build_index, dataset.py:128-137).  For sample s = (sample_date[s],
+ * sample_inst[s]) writes row_index[s][t] = idx_mat[date - T + 1 + t][inst] (dates before the first
+ * one count as missing, dataset.py:141-143), then fill_mode FVAE_FILL_NONE | _FFILL | _FFILL_BFILL
+ * (np_ffill, dataset.py:24-39,145-148); what is still missing becomes `nan_row` (the all-NaN
+ * sentinel row, dataset.py:81-84,172).  If `label` (one value per table row) and `y` are given,
+ * y[s] = label[row_index[s][T-1]] (the reference's returns[:, -1]).                                */
+#define FVAE_FILL_NONE 0
+#define FVAE_FILL_FFILL 1
+#define FVAE_FILL_FFILL_BFILL 2
+int fvae_window_index(const int32_t* idx_mat, int32_t D, int32_t I, const int32_t* sample_date,
+                      const int32_t* sample_inst, int64_t S, int32_t T, int32_t fill_mode, int32_t nan_row,
+                      int32_t* row_index, const float* label, float* y, void* stream);
+/* materialise out[S][T][C] (contiguous, out_dtype FVAE_F32 | FVAE_BF16) from a resident panel -- for
+ * callers that still want the reference's window tensor (DataLoader batch, train_model.py:17-19).   */
+int fvae_gather_windows(const fvae_panel* panel, int64_t S, int32_t T, int32_t C, void* out, int32_t out_dtype,
+                        void* stream);
 
 #ifdef __cplusplus
 }
