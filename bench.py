@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--panel", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-resident", action="store_true", help="skip the resident-panel variant of the end-to-end measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -303,6 +304,47 @@ def main():
                "d2h_bytes_per_step": 4, "host_panel_dtype": "float32", "h2d_gbs": h2d32 / (ms32 * 1e-3) / 1e9,
                "overlap": "H2D of step i+1 on a copy stream under the compute of step i",
                "bf16_host_panel": {"value": world * S / (ms16 * 1e-3), "ms_per_step": ms16, "h2d_bytes_per_step": h2d16}}
+
+    # ---- the same step fed from a RESIDENT row table: the (date, instrument) rows are uploaded once (not
+    # timed, like the reference's one-time pickle load); per step the host sends only the batch's date numbers, one kernel
+    # builds the look-back row index (TSDataSampler._get_indices) and the ELBO kernels read the rows in place.
+    if e2e is not None and not args.no_resident:
+        import numpy as np
+        from factorvae_b200.panel import PanelIndex, ResidentPanel
+        Dn = B + T - 1
+        idx_mat = np.arange(Dn * N, dtype=np.int32).reshape(Dn, N)
+        sd = np.repeat(np.arange(T - 1, Dn, dtype=np.int32), N)
+        sj = np.tile(np.arange(N, dtype=np.int32), B)
+        pidx = PanelIndex(idx_mat, sd, sj, np.arange(0, (B + 1) * N, N), Dn * N)
+        grow = torch.Generator(device="cpu").manual_seed(99 + rank)
+        vals = torch.randn(Dn * N, C_FEATURES + 1, generator=grow).clamp_(-3, 3).numpy()
+        rp = ResidentPanel(vals, pidx, C_FEATURES, dev, dtype=pdt)
+        dates_h = torch.arange(B, dtype=torch.int32).pin_memory()
+        dates_d = torch.empty(B, dtype=torch.int32, device=dev)
+        loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def resident_step():
+            dates_d.copy_(dates_h, non_blocking=True)                      # the step's host input: which dates
+            xw, yw, pw = rp.batch(range(B), T)                            # window-index kernel (+ labels)
+            stepper.step(xw, yw, pw, global_dates=B * world, unit_base=unit_base, train=True)
+            loss_h.copy_(stepper.loss.reshape(1), non_blocking=True)      # D2H of the loss
+        for _ in range(3):
+            resident_step()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(n_e2e):
+            resident_step()
+        r1.record()
+        barrier()
+        t3 = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        msr = float(t3.item()) / n_e2e
+        e2e["resident_panel"] = {"value": world * S / (msr * 1e-3), "ms_per_step": msr, "h2d_bytes_per_step": B * 4 + (B + 1) * 4,
+                                 "d2h_bytes_per_step": 4, "table_mb": rp.table.numel() * rp.table.element_size() / 1e6,
+                                 "note": "row table uploaded once (untimed); per step: date ids H2D, fvae_window_index, "
+                                         "ELBO step reading rows through fvae_panel.row_index, loss D2H"}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
