@@ -89,6 +89,10 @@ def lib() -> C.CDLL:
     L.fvae_window_index.argtypes = [vp, i32, i32, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]
     L.fvae_gather_windows.restype = C.c_int
     L.fvae_gather_windows.argtypes = [C.POINTER(Panel), i64, i32, i32, vp, i32, vp]
+    L.fvae_rank_ic.restype = C.c_int
+    L.fvae_rank_ic.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    L.fvae_adam_step.restype = C.c_int
+    L.fvae_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_float, vp]
     if L.fvae_abi_version() != ABI_VERSION:
         raise ImportError("libfvae_b200.so has an unexpected ABI version")
     _lib = L
@@ -97,7 +101,7 @@ def lib() -> C.CDLL:
 
 EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_debug_front_forward", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
            "fvae_elbo_forward", "fvae_elbo_backward", "fvae_predict", "fvae_fe_forward", "fvae_fe_backward",
-           "fvae_workspace_latent", "fvae_window_index", "fvae_gather_windows"]
+           "fvae_workspace_latent", "fvae_window_index", "fvae_gather_windows", "fvae_adam_step", "fvae_rank_ic"]
 
 
 class FvaeError(RuntimeError):

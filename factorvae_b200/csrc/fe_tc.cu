@@ -633,7 +633,7 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
     const int nsm = num_sms();
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
-    const size_t tail = (CP + NC + 2 * NSPLIT * TM) * 4 + 64;
+    const size_t tail = (CP + NC + 2 * NSPLIT * TM) * 4 + TM + 64;
     const size_t with_stage = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + STAGE_BYTES + tail;
     a.prefetch = (x.dtype == FVAE_BF16 && with_stage <= kMaxSmem) ? 1 : 0;
     const size_t smem = a.prefetch ? with_stage : W1_BYTES + size_t(KCH) * NC * 16 + A_BYTES + STAGE_BYTES + tail;

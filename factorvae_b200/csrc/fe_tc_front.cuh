@@ -76,8 +76,12 @@ struct Rows { static constexpr int PER_PASS = sizeof(XT) == 2 ? TM : TM / 2; };
 // rows [r0, r0 + PER_PASS) of item (st, t) -> slots (zero rows beyond S); one warp per row, asynchronous.
 // Fast path (every row of the pass exists and no 16-byte window can cross the end of the panel): lane = piece,
 // pointer increments only.
+// Resident panel: sOff[row] receives the 16-byte misalignment of the row's source (LayerNorm needs it; it would cost a
+// dependent index load there); *carry / next_item: this lane's table row for the NEXT item of the CTA is fetched here,
+// one item ahead, so the index load never sits in front of the cp.async issue.
 template <typename XT>
-__device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, int t, unsigned char* stage, int r0) {
+__device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, int t, unsigned char* stage, int r0,
+                                                unsigned char* sOff = nullptr, int32_t* carry = nullptr, int64_t next_item = -1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, C = a.C;
     const uint32_t slot = slot_bytes<XT>(C);
     const int npieces = int(slot / 16);
@@ -102,26 +106,41 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
         // resident panel: lane k of the warp fetches the table row of the warp's k-th sequence, one shuffle per row after
         constexpr int RPW = Rows<XT>::PER_PASS / NW;
         int32_t myidx = -1;
-        {
+        if (carry && *carry != INT32_MIN) myidx = *carry;       // fetched while the previous item was being issued
+        else {
             const int64_t s = s0 + warp + int64_t(lane) * NW;
             if (lane < RPW && s < a.S) myidx = a.row_index[s * a.T + t];
         }
-#pragma unroll
+        // compact loop (not unrolled): the kernel is instruction-cache sensitive
+        const uint32_t dst0 = smem_u32(stage) + uint32_t(warp) * slot + uint32_t(lane) * 16u;
+#pragma unroll 1
         for (int k = 0; k < RPW; ++k) {
             const int32_t idx = __shfl_sync(0xffffffffu, myidx, k);
-            unsigned char* dst = stage + size_t(warp + k * NW) * slot;
-            if (idx >= 0) {
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + int64_t(idx) * a.row_pitch);
-                const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
-                if (a0 + slot <= x_end) {
-                    for (int pc = lane; pc < npieces; pc += 32) cp_async16(smem_u32(dst + pc * 16), a0 + pc * 16);
-                } else {
-                    XT* d2 = reinterpret_cast<XT*>(dst + (src - a0));
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + int64_t(idx < 0 ? 0 : idx) * a.row_pitch);
+            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
+            const uint32_t dst = dst0 + uint32_t(k * NW) * slot;
+            if (sOff && lane == 0) sOff[warp + k * NW] = idx < 0 ? 0 : static_cast<unsigned char>(src - a0);
+            if (idx >= 0 && a0 + slot <= x_end && npieces <= 64) {
+                if (lane < npieces) cp_async16(dst, a0 + lane * 16);
+                if (lane + 32 < npieces) cp_async16(dst + 512u, a0 + lane * 16 + 512);
+            } else {                                                // sequence beyond S, or the last table row: plain stores
+                unsigned char* d = stage + size_t(warp + k * NW) * slot;
+                for (int pc = lane; pc < npieces; pc += 32) *reinterpret_cast<uint4*>(d + pc * 16) = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+                if (idx >= 0) {
+                    XT* d2 = reinterpret_cast<XT*>(d + (src - a0));
                     for (int c = lane; c < C; c += 32) d2[c] = reinterpret_cast<const XT*>(src)[c];
                 }
-            } else {
-                for (int pc = lane; pc < npieces; pc += 32) *reinterpret_cast<uint4*>(dst + pc * 16) = make_uint4(0, 0, 0, 0);
             }
+        }
+        if (carry) {
+            int32_t nx = INT32_MIN;
+            if (next_item >= 0) {
+                nx = -1;
+                const int64_t s = (next_item / a.T) * TM + r0 + warp + int64_t(lane) * NW;
+                if (lane < RPW && s < a.S) nx = a.row_index[s * a.T + next_item % a.T];
+            }
+            *carry = nx;
         }
         return;
     }
@@ -222,7 +241,9 @@ __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, in
     float v[HALF_COLS];
     if (active) {
         const int64_t s = st * TM + row;
-        const uint32_t off = s < a.S ? uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u) : 0u;
+        uint32_t off = 0u;
+        if (s < a.S) off = a.row_index ? uint32_t(reinterpret_cast<const unsigned char*>(sStat + 2 * NSPLIT * TM)[row - r0])
+                                       : uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u);
         fetch_half(static_cast<const XT*>(nullptr), stage + size_t(row - r0) * slot_bytes<XT>(C), off, half, v);
         if (partial) {
             if (tail_only) {
@@ -267,8 +288,9 @@ __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, in
 
 // all loads of one item (bf16: one pass; fp32: the given pass), committed as ONE cp.async group
 template <typename XT>
-__device__ __forceinline__ void issue_item_loads(const ItemArgs& a, int64_t item, unsigned char* stage, int r0) {
-    load_rows_async<XT>(a, item / a.T, int(item % a.T), stage, r0);
+__device__ __forceinline__ void issue_item_loads(const ItemArgs& a, int64_t item, unsigned char* stage, int r0,
+                                                 unsigned char* sOff = nullptr, int32_t* carry = nullptr, int64_t next_item = -1) {
+    load_rows_async<XT>(a, item / a.T, int(item % a.T), stage, r0, sOff, carry, next_item);
     cp_async_commit();
 }
 // my share of a [NCH x 128 x 16 B] operand tile in HBM -> shared memory, as one cp.async group
@@ -286,7 +308,7 @@ __device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t i
     const int t = int(item % a.T);
     for (int r0 = 0; r0 < TM; r0 += Rows<XT>::PER_PASS) {
         if (r0 > 0) __syncthreads();
-        if (!(already_issued && r0 == 0)) { load_rows_async<XT>(a, st, t, stage, r0); cp_async_commit(); }
+        if (!(already_issued && r0 == 0)) { load_rows_async<XT>(a, st, t, stage, r0, reinterpret_cast<unsigned char*>(sStat + 2 * NSPLIT * TM)); cp_async_commit(); }
         if (allow_pending && r0 == 0 && already_issued) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
         layernorm_pass<XT>(a, st, t, stage, r0, tile, sStat);
@@ -344,7 +366,8 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     float* sB1 = reinterpret_cast<float*>(sTail);
     float* sBgi = sB1 + CP;
     float* sStat = sBgi + NC;                    // [2][NSPLIT][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * NSPLIT * TM);
+    unsigned char* sOff = reinterpret_cast<unsigned char*>(sStat + 2 * NSPLIT * TM);     // [128] source misalignment per row
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOff + TM);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
     copy_image(sW1, a.ws.w1g, W1_BYTES);
@@ -396,19 +419,20 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     };
     const int64_t G = gridDim.x;
     uint32_t phase = 0;
+    int32_t carry = INT32_MIN;                      // resident panel: my lane's table row of the next item (INT32_MIN: none)
     if (prefetch) {
         // Software pipeline over items (dedicated raw-row stage):  GEMM2(k) runs under LayerNorm(k+1),
         // GEMM1(k+1) under the GI epilogue of k, and the rows of k+2 stream in under both.
         int64_t item = blockIdx.x;
         if (item < nitems) {
-            issue_item_loads<XT>(a, item, sStage, 0);
+            issue_item_loads<XT>(a, item, sStage, 0, sOff, &carry, item + G < nitems ? item + G : -1);
             stage_and_normalize<XT>(a, item, sStage, sA1, sStat, true);
             save_xhat(item);
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
             issue_gemm1();
-            if (item + G < nitems) issue_item_loads<XT>(a, item + G, sStage, 0);
+            if (item + G < nitems) issue_item_loads<XT>(a, item + G, sStage, 0, sOff, &carry, item + 2 * G < nitems ? item + 2 * G : -1);
         }
         for (; item < nitems; item += G, phase ^= 1) {
             mbar_wait(&bars[0], phase);
@@ -427,7 +451,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
                 tc_fence_before_sync();
                 __syncthreads();
                 issue_gemm1();
-                if (nxt + G < nitems) issue_item_loads<XT>(a, nxt + G, sStage, 0);
+                if (nxt + G < nitems) issue_item_loads<XT>(a, nxt + G, sStage, 0, sOff, &carry, nxt + 2 * G < nitems ? nxt + 2 * G : -1);
             }
             mbar_wait(&bars[1], phase);
             tc_fence_after_sync();

@@ -184,6 +184,22 @@ int fvae_window_index(const int32_t* idx_mat, int32_t D, int32_t I, const int32_
 int fvae_gather_windows(const fvae_panel* panel, int64_t S, int32_t T, int32_t C, void* out, int32_t out_dtype,
                         void* stream);
 
+/* ---- fused optimizer step over the flat buffers (replaces optimizer.step() of main.py:60 /
+ *      train_model.py:30: torch.optim.Adam, single-tensor arithmetic, amsgrad off).  `step` is 1-based.
+ *      grad_scale multiplies the gradient first (1.0, or 1/world after a SUM all-reduce).  All four
+ *      buffers 16-byte aligned, n = fvae_param_count().  The per-batch CosineAnnealingLR of
+ *      main.py:61 is a host formula: lr_t = eta_min + (lr0 - eta_min) * (1 + cos(pi t / T_max)) / 2.  */
+int fvae_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                   void* stream);
+
+/* ---- evaluation metric: per-date Spearman rank correlation of predictions and labels (replaces the
+ *      per-date pandas .rank() + scipy.stats.spearmanr loop of utils.py:113-129).  ric[d] for the dates of
+ *      date_ptr (CSR, B+1); average ranks for ties; NaN input, < 2 stocks or a constant column -> NaN.
+ *      max_per_date >= the largest date (<= 4096).  RankIC = mean(ric), RankIC_IR = mean / std (ddof 0). */
+int fvae_rank_ic(const float* pred, const float* label, const int32_t* date_ptr, int32_t B, int32_t max_per_date,
+                 float* ric, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
