@@ -12,6 +12,7 @@
 struct ItemArgs {
     const void* x; int64_t seq_pitch, row_pitch;
     const int32_t* row_index; int64_t num_rows;       // resident panel (NULL: dense windows)
+    int items32;                                      // NT * T < 2^31: item arithmetic in 32 bits
     int S, T, C, H, NC, HP; int64_t NT;
     int prefetch;            // 1: dedicated raw-row stage, next item's rows are fetched during this item's MMAs
     TcWs ws;
@@ -72,6 +73,12 @@ __device__ __forceinline__ const unsigned char* panel_end(const ItemArgs& a) {
 }
 template <typename XT>
 struct Rows { static constexpr int PER_PASS = sizeof(XT) == 2 ? TM : TM / 2; };
+// item -> (tile, time step).  Items fit 32 bits in every supported workload (the host checks): a 64-bit integer division
+// costs ~100 instructions per thread, and this kernel is issue-bound.
+__device__ __forceinline__ void split_item(const ItemArgs& a, int64_t item, int64_t& st, int& t) {
+    if (a.items32) { const uint32_t q = uint32_t(item) / uint32_t(a.T); st = q; t = int(uint32_t(item) - q * uint32_t(a.T)); }
+    else { st = item / a.T; t = int(item % a.T); }
+}
 
 // rows [r0, r0 + PER_PASS) of item (st, t) -> slots (zero rows beyond S); one warp per row, asynchronous.
 // Fast path (every row of the pass exists and no 16-byte window can cross the end of the panel): lane = piece,
@@ -111,25 +118,36 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
             const int64_t s = s0 + warp + int64_t(lane) * NW;
             if (lane < RPW && s < a.S) myidx = a.row_index[s * a.T + t];
         }
-        // compact loop (not unrolled): the kernel is instruction-cache sensitive
-        const uint32_t dst0 = smem_u32(stage) + uint32_t(warp) * slot + uint32_t(lane) * 16u;
-#pragma unroll 1
-        for (int k = 0; k < RPW; ++k) {
-            const int32_t idx = __shfl_sync(0xffffffffu, myidx, k);
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + int64_t(idx < 0 ? 0 : idx) * a.row_pitch);
+        // lane k prepares row k (address, alignment, which path), the warp then walks the rows with three shuffles each:
+        // the kernel is issue-bound, so the per-row scalar work must not be replicated over 32 lanes
+        unsigned long long my_a0 = 0ull;
+        uint32_t my_kind = 0u, my_off = 0u;              // kind 0: zero rows (beyond S), 1: cp.async window, 2: plain loads
+        if (lane < RPW && myidx >= 0) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(static_cast<const XT*>(a.x) + int64_t(myidx) * a.row_pitch);
             const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(15));
+            my_a0 = reinterpret_cast<unsigned long long>(a0);
+            my_off = uint32_t(src - a0);
+            my_kind = (a0 + slot <= x_end && npieces <= 64) ? 1u : 2u;
+        }
+        if (sOff && lane < RPW) sOff[warp + lane * NW] = static_cast<unsigned char>(my_off);
+        const uint32_t dst0 = smem_u32(stage) + uint32_t(warp) * slot + uint32_t(lane) * 16u;
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) {
+            const unsigned char* a0 = reinterpret_cast<const unsigned char*>(__shfl_sync(0xffffffffu, my_a0, k));
+            const uint32_t kind = __shfl_sync(0xffffffffu, my_kind, k);
             const uint32_t dst = dst0 + uint32_t(k * NW) * slot;
-            if (sOff && lane == 0) sOff[warp + k * NW] = idx < 0 ? 0 : static_cast<unsigned char>(src - a0);
-            if (idx >= 0 && a0 + slot <= x_end && npieces <= 64) {
+            if (kind == 1u) {
                 if (lane < npieces) cp_async16(dst, a0 + lane * 16);
                 if (lane + 32 < npieces) cp_async16(dst + 512u, a0 + lane * 16 + 512);
             } else {                                                // sequence beyond S, or the last table row: plain stores
                 unsigned char* d = stage + size_t(warp + k * NW) * slot;
                 for (int pc = lane; pc < npieces; pc += 32) *reinterpret_cast<uint4*>(d + pc * 16) = make_uint4(0, 0, 0, 0);
                 __syncwarp();
-                if (idx >= 0) {
-                    XT* d2 = reinterpret_cast<XT*>(d + (src - a0));
-                    for (int c = lane; c < C; c += 32) d2[c] = reinterpret_cast<const XT*>(src)[c];
+                if (kind == 2u) {
+                    const uint32_t off = __shfl_sync(0xffffffffu, my_off, k);
+                    XT* d2 = reinterpret_cast<XT*>(d + off);
+                    const XT* srcx = reinterpret_cast<const XT*>(a0 + off);
+                    for (int c = lane; c < C; c += 32) d2[c] = srcx[c];
                 }
             }
         }
@@ -137,8 +155,10 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
             int32_t nx = INT32_MIN;
             if (next_item >= 0) {
                 nx = -1;
-                const int64_t s = (next_item / a.T) * TM + r0 + warp + int64_t(lane) * NW;
-                if (lane < RPW && s < a.S) nx = a.row_index[s * a.T + next_item % a.T];
+                int64_t nst; int nt;
+                split_item(a, next_item, nst, nt);
+                const int64_t s = nst * TM + r0 + warp + int64_t(lane) * NW;
+                if (lane < RPW && s < a.S) nx = a.row_index[s * a.T + nt];
             }
             *carry = nx;
         }
@@ -290,7 +310,9 @@ __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, in
 template <typename XT>
 __device__ __forceinline__ void issue_item_loads(const ItemArgs& a, int64_t item, unsigned char* stage, int r0,
                                                  unsigned char* sOff = nullptr, int32_t* carry = nullptr, int64_t next_item = -1) {
-    load_rows_async<XT>(a, item / a.T, int(item % a.T), stage, r0, sOff, carry, next_item);
+    int64_t st; int t;
+    split_item(a, item, st, t);
+    load_rows_async<XT>(a, st, t, stage, r0, sOff, carry, next_item);
     cp_async_commit();
 }
 // my share of a [NCH x 128 x 16 B] operand tile in HBM -> shared memory, as one cp.async group
@@ -304,8 +326,8 @@ __device__ __forceinline__ void issue_tile_load(unsigned char* dst, const unsign
 template <typename XT>
 __device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t item, unsigned char* stage, unsigned char* tile,
                                                     float* sStat, bool already_issued, bool allow_pending = false) {
-    const int64_t st = item / a.T;
-    const int t = int(item % a.T);
+    int64_t st; int t;
+    split_item(a, item, st, t);
     for (int r0 = 0; r0 < TM; r0 += Rows<XT>::PER_PASS) {
         if (r0 > 0) __syncthreads();
         if (!(already_issued && r0 == 0)) { load_rows_async<XT>(a, st, t, stage, r0, reinterpret_cast<unsigned char*>(sStat + 2 * NSPLIT * TM)); cp_async_commit(); }
