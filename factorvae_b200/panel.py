@@ -107,7 +107,14 @@ class ResidentPanel:
         vals = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32))
         feat = torch.cat([vals[:, :num_features], torch.full((1, num_features), float("nan"))], dim=0)
         lab = torch.cat([vals[:, label_col], torch.full((1,), float("nan"))], dim=0)
-        self.table = feat.to(device=dev, dtype=dtype).contiguous()              # (R + 1, C), last row = NaN sentinel
+        # row pitch padded to 16 bytes: every row then starts 16-byte aligned, so the staging kernel sees ONE alignment
+        # case for the whole warp (with the natural 316-byte pitch consecutive rows cycle through four, and the realign
+        # switch of K1 diverges four ways)
+        per16 = 16 // torch.empty((), dtype=dtype).element_size()
+        pitch = (num_features + per16 - 1) // per16 * per16
+        table = torch.zeros(feat.shape[0], pitch, dtype=dtype, device=dev)
+        table[:, :num_features] = feat.to(device=dev, dtype=dtype)
+        self.table = table                                                       # (R + 1, pitch >= C), last row = NaN sentinel
         self.label = lab.to(device=dev, dtype=torch.float32).contiguous()       # (R + 1,)
         self.idx_mat = torch.from_numpy(index.idx_mat).to(dev)
         self.sample_date = torch.from_numpy(index.sample_date).to(dev)
