@@ -304,13 +304,17 @@ def test_bf16_tc_chain_vs_fp32_kernels(shape, cuda_device):
     assert float((g16.double() - g32.double()).norm() / g32.double().norm()) <= 3e-2
 
 
-@pytest.mark.parametrize("case", ["ragged", "many_dates", "one_date_many_tiles", "guard"])
+@pytest.mark.parametrize("case", ["ragged", "many_dates", "one_date_many_tiles", "guard", "max_shape", "tiny_shape"])
 def test_bf16_tc_heads_sweep_sections_vs_fp32_kernels(case, cuda_device):
     """The tcgen05 backward sweep of the heads (heads_tc.cu) against the fp32 CUDA-core chain, per parameter section:
     ragged dates (tile tails, 1-stock dates), more dates than CTAs, one date spanning many tiles, a tripped guard."""
     from factorvae_b200 import engine
     import factorvae_b200 as fb
     H, K, T = 20, 20, 3
+    if case == "max_shape":        # the largest shape the tensor-core heads take: 224 static + 32 per-date columns
+        H, K = 31, 32
+    elif case == "tiny_shape":     # one 8-column group per kind
+        H, K = 5, 3
     torch.manual_seed(23)
     m = fb.FactorVAE(fb.FeatureExtractor(158, H), fb.FactorEncoder(K, 128, H),
                      fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, K)), fb.FactorPredictor(H, K))
@@ -320,7 +324,7 @@ def test_bf16_tc_heads_sweep_sections_vs_fp32_kernels(case, cuda_device):
     L = engine.ParamLayout(158, H, K, 128)
     flat = L.pack(sd, cuda_device)
     counts = {"ragged": [1, 128, 129, 300, 77, 256, 5], "many_dates": [9] * 400, "one_date_many_tiles": [2000],
-              "guard": [150, 90]}[case]
+              "guard": [150, 90], "max_shape": [200, 130, 64], "tiny_shape": [140, 260]}[case]
     ptr = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=cuda_device)
     S = int(ptr[-1])
     g = torch.Generator(device=cuda_device).manual_seed(4)
