@@ -85,7 +85,8 @@ TcWs carve_tc(const FeDims& d, void* base) {
     w.gi = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(NC / 8) * TILE_CH));
     w.hall = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(HP / 8) * TILE_CH));
     w.xh = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(A_BYTES)));
-    w.u = reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(A_BYTES)));
+    // u tiles are saved only when backward cannot rebuild them (tc_wih_recompute_kernel covers NC <= 128)
+    w.u = NC <= 128 ? nullptr : reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(A_BYTES)));
     w.mask = reinterpret_cast<unsigned long long*>(take(NT * d.T * int64_t(4 * TM * 8)));
     w.q = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
     w.dwih = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
@@ -706,6 +707,15 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
 #undef FVAE_LAUNCH_Q
         if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
     }
+    if (NC <= 128) {   // dWih with u rebuilt from the saved xhat tiles (forward did not store u)
+        const size_t g_bytes = size_t(NC / 8) * TILE_CH;
+        const size_t smemw = 2 * size_t(A_BYTES) + 2 * g_bytes + A_BYTES + W1_BYTES + 128;
+        if (smemw > kMaxSmem) return FVAE_ERR_LIMIT;
+        cudaError_t ce2;
+        if ((ce2 = cudaFuncSetAttribute(tc_wih_recompute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemw))) != cudaSuccess) return int(ce2);
+        tc_wih_recompute_kernel<<<grid, WR_THREADS, smemw, st>>>(a); count_launch();
+        if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
+    } else
     {   // dWih from the u tiles saved by the forward kernel (the panel is not touched)
         const size_t per_stage = size_t(NC / 8) * TILE_CH + A_BYTES;
         cudaError_t ce2;

@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
         for (; item < nitems; item += G, phase ^= 1) {
             mbar_wait(&bars[0], phase);
             tc_fence_after_sync();
-            epilogue_u(tmem, lane_base, half, row, C, sA2, reinterpret_cast<unsigned char*>(a.ws.u) + size_t(item) * A_BYTES,
+            epilogue_u(tmem, lane_base, half, row, C, sA2, a.ws.u ? reinterpret_cast<unsigned char*>(a.ws.u) + size_t(item) * A_BYTES : nullptr,
                        a.ws.mask + size_t(item) * 4 * TM);
             fence_async_smem();
             tc_fence_before_sync();
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
             issue_gemm1();
             mbar_wait(&bars[0], phase);
             tc_fence_after_sync();
-            epilogue_u(tmem, lane_base, half, row, C, sA2, reinterpret_cast<unsigned char*>(a.ws.u) + size_t(item) * A_BYTES,
+            epilogue_u(tmem, lane_base, half, row, C, sA2, a.ws.u ? reinterpret_cast<unsigned char*>(a.ws.u) + size_t(item) * A_BYTES : nullptr,
                        a.ws.mask + size_t(item) * 4 * TM);
             fence_async_smem();
             tc_fence_before_sync();
@@ -877,6 +877,132 @@ __global__ void __launch_bounds__(QS_THREADS, 1) tc_q_stream_kernel(ItemArgs a) 
                     const int o = 128 + 8 * half + e;
                     if (o < C) atomicAdd(a.ws.q + size_t(o) * CP + i, d[e]);
                 }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---- K4b (recompute variant, NC <= 128): dW_ih += dGI^T [u | 1] with u = LeakyReLU(xhat W1g^T + b1f) REBUILT from the saved
+// xhat tile, so the forward kernel does not have to write the u tiles at all (40 KB per item, 29 % of K1's HBM traffic;
+// K1 is HBM-write bound).  Same bytes in as the streaming variant (xhat instead of u), one extra UMMA group (GEMM1,
+// 128x160x160) and the LeakyReLU epilogue per item -- both hidden behind the HBM stream:
+//   issuer warp : bulk copies (xhat 2 stages, dGI 2 stages), GEMM1(k+1) -> PRE[(k+1)&1] one item ahead,
+//                 weight-gradient UMMAs of item k once the epilogue threads have written u(k)
+//   512 threads : PRE[k&1] -> LeakyReLU -> bf16 u tile (identical to K1's epilogue_u: same rounding, ones column at C)
+constexpr int WR_THREADS = NTH + 32;
+__global__ void __launch_bounds__(WR_THREADS, 1) tc_wih_recompute_kernel(ItemArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
+    const int NC = a.NC, NCH = NC / 8, C = a.C;
+    const uint32_t g_bytes = uint32_t(NCH) * TILE_CH;
+    unsigned char* sX = smem;                                   // [2][A_BYTES] xhat stages
+    unsigned char* sG = sX + 2 * A_BYTES;                       // [2][g_bytes] dGI stages; the M-block over-read runs into what follows
+    unsigned char* sU = sG + 2 * g_bytes;                       // u tile
+    unsigned char* sW1 = sU + A_BYTES;                          // W1g image (bias column folded)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW1 + W1_BYTES);
+    uint64_t* full_x = bars;            // [2]
+    uint64_t* full_g = bars + 2;        // [2]
+    uint64_t* bar_pre = bars + 4;       // [2] GEMM1 into PRE[i] complete
+    uint64_t* bar_w = bars + 6;         // weight-gradient UMMAs of the last issued item complete
+    uint64_t* u_ready = bars + 7;       // all epilogue threads wrote their part of u (and read PRE)
+    uint64_t* fin = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const bool issuer = warp == NTH / 32;
+    copy_image(sW1, a.ws.w1g, W1_BYTES);
+    for (uint32_t i = tid; i < (2 * A_BYTES + 2 * g_bytes + A_BYTES) / 16; i += WR_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { for (int i = 0; i < 9; ++i) mbar_init(&bars[i], 1); mbar_init(u_ready, NTH); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+    constexpr uint32_t COL_PRE = 0, COL_DW = 320;              // PRE[0] [0,160) | PRE[1] [160,320) | dW_ih [320,480)
+    const int64_t nitems = a.NT * a.T, G = gridDim.x;
+    const int64_t mine = nitems > int64_t(blockIdx.x) ? (nitems - 1 - blockIdx.x) / G + 1 : 0;
+    if (mine > 0 && issuer) {
+        if ((tid & 31) == 0) {
+            auto load_x = [&](int64_t k) {
+                mbar_expect_tx(&full_x[k & 1], A_BYTES);
+                bulk_g2s(sX + (k & 1) * A_BYTES, reinterpret_cast<const unsigned char*>(a.ws.xh) + size_t(blockIdx.x + k * G) * A_BYTES, A_BYTES, &full_x[k & 1]);
+            };
+            auto load_g = [&](int64_t k) {
+                mbar_expect_tx(&full_g[k & 1], g_bytes);
+                bulk_g2s(sG + (k & 1) * g_bytes, reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(blockIdx.x + k * G) * g_bytes, g_bytes, &full_g[k & 1]);
+            };
+            auto issue_pre = [&](int64_t k) {                   // GEMM1 of item k into PRE[k & 1]
+                mbar_wait(&full_x[k & 1], uint32_t(k >> 1) & 1u);
+                tc_fence_after_sync();
+                issue_row_gemm(tmem, COL_PRE + uint32_t(k & 1) * CP, smem_u32(sX + (k & 1) * A_BYTES), smem_u32(sW1), CP, CP, KCH / 2);
+                mma_commit(&bar_pre[k & 1]);
+            };
+            load_x(0); load_g(0);
+            if (mine > 1) { load_x(1); load_g(1); }
+            issue_pre(0);
+            for (int64_t k = 0; k < mine; ++k) {
+                // PRE[(k+1)&1] was last read by the epilogue of item k-1, which has signalled u_ready(k-1) (waited below, last turn)
+                if (k + 1 < mine) issue_pre(k + 1);
+                if (k + 2 < mine) {                             // xhat stage k&1 is free as soon as GEMM1(k) has completed
+                    mbar_wait(&bar_pre[k & 1], uint32_t(k >> 1) & 1u);
+                    load_x(k + 2);
+                }
+                mbar_wait(u_ready, uint32_t(k) & 1u);           // u(k) is in shared memory, PRE[k&1] has been read
+                mbar_wait(&full_g[k & 1], uint32_t(k >> 1) & 1u);
+                tc_fence_after_sync();
+                issue_wgrad(tmem, COL_DW, smem_u32(sG + (k & 1) * g_bytes), 0, smem_u32(sU), CP, k > 0);
+                mma_commit(bar_w);
+                if (k + 2 < mine) {                             // dGI stage k&1 is free once these UMMAs are done
+                    mbar_wait(bar_w, uint32_t(k) & 1u);
+                    load_g(k + 2);
+                }
+            }
+            mma_commit(fin);
+        }
+        __syncwarp();
+    } else if (mine > 0) {
+        for (int64_t k = 0; k < mine; ++k) {
+            mbar_wait(&bar_pre[k & 1], uint32_t(k >> 1) & 1u);
+            tc_fence_after_sync();
+            uint4 pk[HALF_CH];
+            const int c0 = HALF_COLS * half;
+            const int one_ch = (C >= c0 && C < c0 + HALF_COLS) ? (C - c0) >> 3 : -1;
+#pragma unroll
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                float v[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_PRE + uint32_t(k & 1) * CP + c0 + ch * 8), v);
+                uint32_t w0 = lrelu_pack(v[0], v[1]), w1 = lrelu_pack(v[2], v[3]), w2 = lrelu_pack(v[4], v[5]), w3 = lrelu_pack(v[6], v[7]);
+                if (ch == one_ch) {
+                    const int e = (C - c0) & 7, q = e >> 1;
+                    const uint32_t one = 0x3F80u << (16 * (e & 1)), keep = 0xFFFFu << (16 * ((e & 1) ^ 1));
+                    if (q == 0) w0 = (w0 & keep) | one;
+                    else if (q == 1) w1 = (w1 & keep) | one;
+                    else if (q == 2) w2 = (w2 & keep) | one;
+                    else w3 = (w3 & keep) | one;
+                }
+                pk[ch] = make_uint4(w0, w1, w2, w3);
+            }
+            if (k > 0) mbar_wait(bar_w, uint32_t(k - 1) & 1u);  // the UMMAs that read u(k-1) are done: the u tile is free
+#pragma unroll
+            for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sU + tile_off(TM, row, HALF_CH * half + ch)) = pk[ch];
+            fence_async_smem();
+            tc_fence_before_sync();
+            mbar_arrive(u_ready);
+        }
+        mbar_wait(fin, 0);
+        tc_fence_after_sync();
+        // flush dW_ih: lane = permuted gate row, my 40 columns
+#pragma unroll
+        for (int ch = 0; ch < HALF_CH; ++ch) {                  // the TMEM load is warp-collective: every lane issues it
+            const int n0 = HALF_COLS * half + ch * 8;
+            float v[8];
+            tmem_ld8(tmem_addr(tmem, lane_base, COL_DW + n0), v);
+            if (row < NC) {
+                red_add_v4(a.ws.dwih + size_t(row) * CP + n0, v[0], v[1], v[2], v[3]);
+                red_add_v4(a.ws.dwih + size_t(row) * CP + n0 + 4, v[4], v[5], v[6], v[7]);
             }
         }
     }
