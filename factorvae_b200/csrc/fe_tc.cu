@@ -695,10 +695,14 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
             if ((ce2 = cudaFuncSetAttribute(tc_q_from_tiles_kernel<NSTGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemq))) != cudaSuccess) return int(ce2); \
             tc_q_from_tiles_kernel<NSTGV><<<grid, NTH, smemq, st>>>(a); count_launch();                               \
         } while (0)
-        const size_t stream_smem = 2 * size_t(A_BYTES) + 3 * g_bytes + A_BYTES + wt + 128;
-        if (stream_smem <= kMaxSmem) {
-            if ((ce2 = cudaFuncSetAttribute(tc_q_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream_smem))) != cudaSuccess) return int(ce2);
-            tc_q_stream_kernel<<<grid, QS_THREADS, stream_smem, st>>>(a); count_launch();
+        const size_t stream22 = 2 * size_t(A_BYTES) + 2 * g_bytes + 2 * size_t(A_BYTES) + wt + 128;
+        const size_t stream13 = 2 * size_t(A_BYTES) + 3 * g_bytes + A_BYTES + wt + 128;
+        if (stream22 <= kMaxSmem) {
+            if ((ce2 = cudaFuncSetAttribute(tc_q_stream_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream22))) != cudaSuccess) return int(ce2);
+            tc_q_stream_kernel<2, 2><<<grid, QS_THREADS, stream22, st>>>(a); count_launch();
+        } else if (stream13 <= kMaxSmem) {
+            if ((ce2 = cudaFuncSetAttribute(tc_q_stream_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(stream13))) != cudaSuccess) return int(ce2);
+            tc_q_stream_kernel<1, 3><<<grid, QS_THREADS, stream13, st>>>(a); count_launch();
         }
         else if (wt + 3 * per_stage + 64 <= kMaxSmem) FVAE_LAUNCH_Q(3);
         else if (wt + 2 * per_stage + 64 <= kMaxSmem) FVAE_LAUNCH_Q(2);

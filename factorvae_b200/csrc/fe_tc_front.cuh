@@ -759,25 +759,28 @@ __global__ void __launch_bounds__(NTH, 1) tc_q_from_tiles_kernel(ItemArgs a) {
 // used the stage have completed (it is only needed by Q, one and a half iterations later).  du(k+1) is issued in front
 // of Q(k), so the dpre epilogue of item k+1 overlaps the Q MMAs of item k.  Used when the buffers fit (NC <= 96).
 constexpr int QS_THREADS = NTH + 32;          // 512 epilogue threads + one warp that feeds the stages and issues the UMMAs
+// NDP dpre tiles / NG dGI stages: (2, 2) when it fits -- the epilogue of item k+1 then does not wait for the Q MMAs of item k --
+// else (1, 3).
+template <int NDP, int NG>
 __global__ void __launch_bounds__(QS_THREADS, 1) tc_q_stream_kernel(ItemArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
     const int NC = a.NC, NCH = NC / 8;
     const uint32_t g_bytes = uint32_t(NCH) * TILE_CH;
     unsigned char* sX = smem;                                   // [2][A_BYTES]; the M-block over-read of stage 1 runs into sG
-    unsigned char* sG = sX + 2 * A_BYTES;                       // [3][g_bytes]
-    unsigned char* sD = sG + 3 * g_bytes;                       // dpre tile
-    unsigned char* sWihT = sD + A_BYTES;
+    unsigned char* sG = sX + 2 * A_BYTES;                       // [NG][g_bytes]
+    unsigned char* sD = sG + NG * g_bytes;                      // [NDP] dpre tiles
+    unsigned char* sWihT = sD + NDP * A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sWihT + uint32_t(NCH) * CP * 16);
     uint64_t* full_x = bars;            // [2]
-    uint64_t* full_g = bars + 2;        // [3]
+    uint64_t* full_g = bars + 2;        // [NG <= 3]
     uint64_t* bar_du = bars + 5;
     uint64_t* bar_q = bars + 6;         // [2]
     uint64_t* dpre_ready = bars + 8;    // all epilogue threads have written their part of the dpre tile (and read du)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
     const bool issuer = warp == NTH / 32;
     copy_image(sWihT, a.ws.wihT, uint32_t(NCH) * CP * 16);
-    for (uint32_t i = tid; i < (2 * A_BYTES + 3 * g_bytes + A_BYTES) / 16; i += QS_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < (2 * A_BYTES + NG * g_bytes + NDP * A_BYTES) / 16; i += QS_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1); mbar_init(dpre_ready, NTH); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     fence_async_smem();
@@ -796,24 +799,24 @@ __global__ void __launch_bounds__(QS_THREADS, 1) tc_q_stream_kernel(ItemArgs a) 
     };
     auto load_g = [&](int64_t k) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(blockIdx.x + k * G) * g_bytes;
-        mbar_expect_tx(&full_g[k % 3], g_bytes);
-        bulk_g2s(sG + (k % 3) * g_bytes, src, g_bytes, &full_g[k % 3]);
+        mbar_expect_tx(&full_g[k % NG], g_bytes);
+        bulk_g2s(sG + (k % NG) * g_bytes, src, g_bytes, &full_g[k % NG]);
     };
     auto issue_du = [&](int64_t k) {    // one thread; waits for the dGI tile of item k
-        mbar_wait(&full_g[k % 3], uint32_t(k / 3) & 1u);
-        issue_row_gemm(tmem, COL_DU, smem_u32(sG + (k % 3) * g_bytes), smem_u32(sWihT), CP, CP, NC / 16);
+        mbar_wait(&full_g[k % NG], uint32_t(k / NG) & 1u);
+        issue_row_gemm(tmem, COL_DU, smem_u32(sG + (k % NG) * g_bytes), smem_u32(sWihT), CP, CP, NC / 16);
         mma_commit(bar_du);
     };
     if (mine > 0 && issuer) {
         if ((tid & 31) == 0) {
-            load_g(0); if (mine > 1) load_g(1); if (mine > 2) load_g(2);
+            for (int64_t k0 = 0; k0 < NG && k0 < mine; ++k0) load_g(k0);
             load_x(0); if (mine > 1) load_x(1);
             tc_fence_after_sync();
             issue_du(0);
             for (int64_t k = 0; k < mine; ++k) {
                 const bool has_next = k + 1 < mine;
                 mbar_wait(bar_du, uint32_t(k) & 1u);           // du(k) done: its dGI stage is free
-                if (k + 3 < mine) load_g(k + 3);
+                if (k + NG < mine) load_g(k + NG);
                 if (k > 0) {                                   // Q(k-1) done: xhat stage (k-1)&1 is free
                     mbar_wait(&bar_q[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u);
                     if (has_next) load_x(k + 1);
@@ -822,7 +825,7 @@ __global__ void __launch_bounds__(QS_THREADS, 1) tc_q_stream_kernel(ItemArgs a) 
                 tc_fence_after_sync();
                 if (has_next) issue_du(k + 1);                 // in front of Q(k)
                 mbar_wait(&full_x[k & 1], uint32_t(k >> 1) & 1u);
-                const uint32_t xs = smem_u32(sX + (k & 1) * A_BYTES), ds = smem_u32(sD);
+                const uint32_t xs = smem_u32(sX + (k & 1) * A_BYTES), ds = smem_u32(sD + (NDP == 2 ? (k & 1) : 0) * A_BYTES);
                 issue_wgrad(tmem, COL_QA, ds, 0, xs, CP, k > 0);                        // rows o < 128
                 issue_wgrad(tmem, COL_QB0, xs, 0, ds + 16 * TILE_CH, 32, k > 0);         // rows o >= 128, i < 128
                 issue_wgrad(tmem, COL_QB1, xs, 16, ds + 16 * TILE_CH, 32, k > 0);        // rows o >= 128, i >= 128
@@ -847,9 +850,12 @@ __global__ void __launch_bounds__(QS_THREADS, 1) tc_q_stream_kernel(ItemArgs a) 
                 for (int e = 0; e < 8; ++e) d[e] *= ((mbits >> (ch * 8 + e)) & 1ull) ? 1.f : kLeakySlope;
                 pk[ch] = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
             }
-            if (k > 0) mbar_wait(&bar_q[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u);     // Q(k-1) done: the dpre tile is free
+            // my dpre tile is free once the Q MMAs that read it are done: item k-1 with one tile, item k-2 with two
+            if (NDP == 1) { if (k > 0) mbar_wait(&bar_q[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u); }
+            else if (k > 1) mbar_wait(&bar_q[k & 1], uint32_t((k - 2) >> 1) & 1u);
+            unsigned char* sDk = sD + (NDP == 2 ? (k & 1) : 0) * A_BYTES;
 #pragma unroll
-            for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sD + tile_off(TM, row, HALF_CH * half + ch)) = pk[ch];
+            for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sDk + tile_off(TM, row, HALF_CH * half + ch)) = pk[ch];
             fence_async_smem();
             tc_fence_before_sync();
             mbar_arrive(dpre_ready);
