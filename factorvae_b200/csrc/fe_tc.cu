@@ -599,7 +599,8 @@ ItemArgs make_item_args(const FeDims& d, const fvae_panel& x, const TcWs& ws) {
     a.x = x.data; a.seq_pitch = x.seq_pitch; a.row_pitch = x.row_pitch; a.row_index = x.row_index; a.num_rows = x.num_rows;
     a.S = d.S; a.T = d.T; a.C = d.C; a.H = d.H; a.NC = nc_of(d.H); a.HP = hp_of(d.H);
     a.NT = (int64_t(d.S) + TM - 1) / TM;
-    a.items32 = (a.NT * int64_t(d.T) < (int64_t(1) << 31)) ? 1 : 0;
+    a.items32 = (d.T >= 2 && a.NT * int64_t(d.T) * int64_t(d.T) < (int64_t(1) << 32)) ? 1 : 0;
+    a.t_magic = d.T >= 2 ? uint32_t((uint64_t(1) << 32) / uint64_t(d.T)) + 1u : 0u;
     a.prefetch = 0;
     a.ws = ws;
     return a;

@@ -12,7 +12,8 @@
 struct ItemArgs {
     const void* x; int64_t seq_pitch, row_pitch;
     const int32_t* row_index; int64_t num_rows;       // resident panel (NULL: dense windows)
-    int items32;                                      // NT * T < 2^31: item arithmetic in 32 bits
+    int items32;                                      // item arithmetic in 32 bits (NT * T * T < 2^32)
+    uint32_t t_magic;                                 // floor(2^32 / T) + 1
     int S, T, C, H, NC, HP; int64_t NT;
     int prefetch;            // 1: dedicated raw-row stage, next item's rows are fetched during this item's MMAs
     TcWs ws;
@@ -76,8 +77,14 @@ struct Rows { static constexpr int PER_PASS = sizeof(XT) == 2 ? TM : TM / 2; };
 // item -> (tile, time step).  Items fit 32 bits in every supported workload (the host checks): a 64-bit integer division
 // costs ~100 instructions per thread, and this kernel is issue-bound.
 __device__ __forceinline__ void split_item(const ItemArgs& a, int64_t item, int64_t& st, int& t) {
-    if (a.items32) { const uint32_t q = uint32_t(item) / uint32_t(a.T); st = q; t = int(uint32_t(item) - q * uint32_t(a.T)); }
-    else { st = item / a.T; t = int(item % a.T); }
+    if (a.items32) {
+        // multiply-high by magic = floor(2^32 / T) + 1: exact for item * T < 2^32 (the host sets items32 accordingly); the
+        // compare-and-fix keeps it right even at the boundary
+        uint32_t q = __umulhi(uint32_t(item), a.t_magic);
+        uint32_t r = uint32_t(item) - q * uint32_t(a.T);
+        if (r >= uint32_t(a.T)) { ++q; r -= uint32_t(a.T); }
+        st = q; t = int(r);
+    } else { st = item / a.T; t = int(item % a.T); }
 }
 
 // rows [r0, r0 + PER_PASS) of item (st, t) -> slots (zero rows beyond S); one warp per row, asynchronous.
