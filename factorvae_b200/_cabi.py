@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfvae_b200.so")
+# FVAE_B200_LIB: load another build of the same ABI (A/B kernel timing); default: the in-tree library
+LIB_PATH = os.environ.get("FVAE_B200_LIB") or os.path.join(_HERE, "libfvae_b200.so")
 
 F32, BF16 = 0, 1
 PREC_FP32, PREC_BF16_TC = 0, 1

@@ -640,8 +640,15 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
     const size_t with_stage = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + STAGE_BYTES + tail;
     a.prefetch = (x.dtype == FVAE_BF16 && with_stage <= kMaxSmem) ? 1 : 0;
     const size_t smem = a.prefetch ? with_stage : W1_BYTES + size_t(KCH) * NC * 16 + A_BYTES + STAGE_BYTES + tail;
-    if (x.dtype == FVAE_BF16) return launch_smem(tc_front_fwd_kernel<__nv_bfloat16>, grid, smem, st, a);
-    return launch_smem(tc_front_fwd_kernel<float>, grid, smem, st, a);
+    const bool idx = x.row_index != nullptr;
+    if (x.dtype == FVAE_BF16) {
+        if (a.prefetch) return idx ? launch_smem(tc_front_fwd_kernel<__nv_bfloat16, true, true>, grid, smem, st, a)
+                                   : launch_smem(tc_front_fwd_kernel<__nv_bfloat16, false, true>, grid, smem, st, a);
+        return idx ? launch_smem(tc_front_fwd_kernel<__nv_bfloat16, true, false>, grid, smem, st, a)
+                   : launch_smem(tc_front_fwd_kernel<__nv_bfloat16, false, false>, grid, smem, st, a);
+    }
+    return idx ? launch_smem(tc_front_fwd_kernel<float, true, false>, grid, smem, st, a)
+               : launch_smem(tc_front_fwd_kernel<float, false, false>, grid, smem, st, a);
 }
 
 int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, void* wsp, cudaStream_t st) {

@@ -93,7 +93,7 @@ __device__ __forceinline__ void split_item(const ItemArgs& a, int64_t item, int6
 // Resident panel: sOff[row] receives the 16-byte misalignment of the row's source (LayerNorm needs it; it would cost a
 // dependent index load there); *carry / next_item: this lane's table row for the NEXT item of the CTA is fetched here,
 // one item ahead, so the index load never sits in front of the cp.async issue.
-template <typename XT>
+template <typename XT, bool IDX>
 __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, int t, unsigned char* stage, int r0,
                                                 unsigned char* sOff = nullptr, int32_t* carry = nullptr, int64_t next_item = -1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, C = a.C;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
     const int npieces = int(slot / 16);
     constexpr int NW = NTH / 32;
     const int64_t s0 = st * TM + r0;
-    if (!a.row_index && s0 + Rows<XT>::PER_PASS + 1 <= a.S && npieces <= 64) {
+    if (!IDX && s0 + Rows<XT>::PER_PASS + 1 <= a.S && npieces <= 64) {
         const unsigned char* src = row_ptr<XT>(a, s0 + warp, t);
         const int64_t step = a.seq_pitch * int64_t(sizeof(XT)) * NW;
         uint32_t dst = smem_u32(stage) + uint32_t(warp) * slot + uint32_t(lane) * 16u;
@@ -116,7 +116,7 @@ __device__ __forceinline__ void load_rows_async(const ItemArgs& a, int64_t st, i
         return;
     }
     const unsigned char* x_end = panel_end<XT>(a);
-    if (a.row_index) {
+    if (IDX) {
         // resident panel: lane k of the warp fetches the table row of the warp's k-th sequence, one shuffle per row after
         constexpr int RPW = Rows<XT>::PER_PASS / NW;
         int32_t myidx = -1;
@@ -257,9 +257,9 @@ __device__ __forceinline__ void fetch_half(const float*, const unsigned char* sl
 // barrier inside).  Statistics are fp32 sums of x and x^2 over exactly C features (var = E[x^2] - mean^2: the
 // cancellation only bites when |mean| >> std, where bf16 operands have already lost the signal; the fp32 mode
 // keeps the two-pass form).  Only the thread whose 40 columns straddle C pays for masking.
-template <typename XT>
+template <typename XT, bool IDX>
 __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, int t, const unsigned char* stage, int r0,
-                                               unsigned char* tile, float* sStat) {
+                                               unsigned char* tile, float* sStat, unsigned char* gsave = nullptr) {
     const int tid = threadIdx.x, row = tid & (TM - 1), half = tid >> 7, C = a.C;
     const bool active = row >= r0 && row < r0 + Rows<XT>::PER_PASS;
     const int c0 = HALF_COLS * half;
@@ -269,7 +269,7 @@ __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, in
     if (active) {
         const int64_t s = st * TM + row;
         uint32_t off = 0u;
-        if (s < a.S) off = a.row_index ? uint32_t(reinterpret_cast<const unsigned char*>(sStat + 2 * NSPLIT * TM)[row - r0])
+        if (s < a.S) off = IDX ? uint32_t(reinterpret_cast<const unsigned char*>(sStat + 2 * NSPLIT * TM)[row - r0])
                                        : uint32_t(reinterpret_cast<uintptr_t>(row_ptr<XT>(a, s, t)) & 15u);
         fetch_half(static_cast<const XT*>(nullptr), stage + size_t(row - r0) * slot_bytes<XT>(C), off, half, v);
         if (partial) {
@@ -306,20 +306,22 @@ __device__ __forceinline__ void layernorm_pass(const ItemArgs& a, int64_t st, in
             }
         }
 #pragma unroll
-        for (int ch = 0; ch < HALF_CH; ++ch)
-            *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) =
-                make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
-                           pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
+        for (int ch = 0; ch < HALF_CH; ++ch) {
+            const uint4 pk = make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
+                                        pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
+            *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) = pk;
+            if (gsave) *reinterpret_cast<uint4*>(gsave + tile_off(TM, row, HALF_CH * half + ch)) = pk;    // xhat tile, saved for backward
+        }
     }
 }
 
 // all loads of one item (bf16: one pass; fp32: the given pass), committed as ONE cp.async group
-template <typename XT>
+template <typename XT, bool IDX>
 __device__ __forceinline__ void issue_item_loads(const ItemArgs& a, int64_t item, unsigned char* stage, int r0,
                                                  unsigned char* sOff = nullptr, int32_t* carry = nullptr, int64_t next_item = -1) {
     int64_t st; int t;
     split_item(a, item, st, t);
-    load_rows_async<XT>(a, st, t, stage, r0, sOff, carry, next_item);
+    load_rows_async<XT, IDX>(a, st, t, stage, r0, sOff, carry, next_item);
     cp_async_commit();
 }
 // my share of a [NCH x 128 x 16 B] operand tile in HBM -> shared memory, as one cp.async group
@@ -330,17 +332,18 @@ __device__ __forceinline__ void issue_tile_load(unsigned char* dst, const unsign
 
 // stage (unless already issued) + LayerNorm of one item -> xhat tile.  allow_pending: one younger cp.async
 // group (a tile prefetch issued after the rows) may still be in flight.
-template <typename XT>
+template <typename XT, bool IDX>
 __device__ __forceinline__ void stage_and_normalize(const ItemArgs& a, int64_t item, unsigned char* stage, unsigned char* tile,
-                                                    float* sStat, bool already_issued, bool allow_pending = false) {
+                                                    float* sStat, bool already_issued, bool allow_pending = false,
+                                                    unsigned char* gsave = nullptr) {
     int64_t st; int t;
     split_item(a, item, st, t);
     for (int r0 = 0; r0 < TM; r0 += Rows<XT>::PER_PASS) {
         if (r0 > 0) __syncthreads();
-        if (!(already_issued && r0 == 0)) { load_rows_async<XT>(a, st, t, stage, r0, reinterpret_cast<unsigned char*>(sStat + 2 * NSPLIT * TM)); cp_async_commit(); }
+        if (!(already_issued && r0 == 0)) { load_rows_async<XT, IDX>(a, st, t, stage, r0, reinterpret_cast<unsigned char*>(sStat + 2 * NSPLIT * TM)); cp_async_commit(); }
         if (allow_pending && r0 == 0 && already_issued) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
-        layernorm_pass<XT>(a, st, t, stage, r0, tile, sStat);
+        layernorm_pass<XT, IDX>(a, st, t, stage, r0, tile, sStat, gsave);
     }
 }
 
@@ -355,14 +358,17 @@ __device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, in
                                            unsigned char* gtile = nullptr, unsigned long long* gmask = nullptr) {
     const int c0 = HALF_COLS * half;
     const int one_ch = (C >= c0 && C < c0 + HALF_COLS) ? (C - c0) >> 3 : -1;       // warp-uniform
-    unsigned long long bits = 0ull;
+    uint32_t bits_lo = 0u, bits_hi = 0u;           // two 32-bit words: one predicated OR-immediate per column
 #pragma unroll
     for (int ch = 0; ch < HALF_CH; ++ch) {
         float v[8];
         tmem_ld8(tmem_addr(tmem, lane_base, c0 + ch * 8), v);
         if (gmask) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) bits |= (unsigned long long)(v[e] > 0.f) << (ch * 8 + e);
+            for (int e = 0; e < 8; ++e) {          // branch-free: select an immediate, OR it in
+                const uint32_t m = (v[e] > 0.f) ? (1u << (((ch & 3) * 8 + e) & 31)) : 0u;
+                if (ch < 4) bits_lo |= m; else bits_hi |= m;
+            }
         }
         uint32_t w0 = lrelu_pack(v[0], v[1]), w1 = lrelu_pack(v[2], v[3]), w2 = lrelu_pack(v[4], v[5]), w3 = lrelu_pack(v[6], v[7]);
         if (ch == one_ch) {
@@ -377,11 +383,13 @@ __device__ __forceinline__ void epilogue_u(uint32_t tmem, uint32_t lane_base, in
         *reinterpret_cast<uint4*>(tile + tile_off(TM, row, HALF_CH * half + ch)) = pk;
         if (gtile) *reinterpret_cast<uint4*>(gtile + tile_off(TM, row, HALF_CH * half + ch)) = pk;     // saved for backward
     }
-    if (gmask) gmask[half * TM + row] = bits;
+    if (gmask) gmask[half * TM + row] = (unsigned long long)bits_lo | ((unsigned long long)bits_hi << 32);
 }
 
 // ---- K1: front forward ---------------------------------------------------------------------------------------
-template <typename XT>
+// IDX: rows come through fvae_panel.row_index (resident panel); PF: dedicated raw-row stage + software pipeline over items.
+// Compile-time variants: the kernel is instruction-cache sensitive (each one carries only its own staging code).
+template <typename XT, bool IDX, bool PF>
 __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), half = tid >> 7;
@@ -390,8 +398,8 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     unsigned char* sWih = sW1 + W1_BYTES;
     unsigned char* sA1 = sWih + uint32_t(KCH) * NC * 16;
     unsigned char* sA2 = sA1 + A_BYTES;          // u tile; doubles as the raw-row stage when there is no dedicated one
-    unsigned char* sStage = a.prefetch ? sA2 + A_BYTES : sA2;
-    unsigned char* sTail = a.prefetch ? sStage + STAGE_BYTES : sA2 + STAGE_BYTES;
+    unsigned char* sStage = PF ? sA2 + A_BYTES : sA2;
+    unsigned char* sTail = PF ? sStage + STAGE_BYTES : sA2 + STAGE_BYTES;
     float* sB1 = reinterpret_cast<float*>(sTail);
     float* sBgi = sB1 + CP;
     float* sStat = sBgi + NC;                    // [2][NSPLIT][128]
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = uint32_t(warp & 3) * 32u;
     const int64_t nitems = a.NT * a.T;
-    const bool prefetch = a.prefetch != 0 && sizeof(XT) == 2;
+    constexpr bool prefetch = PF && sizeof(XT) == 2;
     // gi = acc + (b_ih [+ b_hr, b_hz]) -> bf16 GI tile (coalesced 16-byte chunks); the column parts split the chunks
     auto epilogue_gi = [&](int64_t item) {
         unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
@@ -438,9 +446,10 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
             mma_commit(&bars[1]);
         }
     };
-    // my 5 chunks of the xhat tile -> HBM (saved for backward); reads what this thread itself wrote
+    // the xhat tile goes to HBM (saved for backward) straight from the registers LayerNorm packs it in
+    auto xh_of = [&](int64_t item) { return reinterpret_cast<unsigned char*>(a.ws.xh) + size_t(item) * A_BYTES; };
     auto save_xhat = [&](int64_t item) {
-        unsigned char* g = reinterpret_cast<unsigned char*>(a.ws.xh) + size_t(item) * A_BYTES;
+        unsigned char* g = xh_of(item);
 #pragma unroll
         for (int ch = 0; ch < HALF_CH; ++ch)
             *reinterpret_cast<uint4*>(g + tile_off(TM, row, HALF_CH * half + ch)) =
@@ -454,14 +463,14 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
         // GEMM1(k+1) under the GI epilogue of k, and the rows of k+2 stream in under both.
         int64_t item = blockIdx.x;
         if (item < nitems) {
-            issue_item_loads<XT>(a, item, sStage, 0, sOff, &carry, item + G < nitems ? item + G : -1);
-            stage_and_normalize<XT>(a, item, sStage, sA1, sStat, true);
+            issue_item_loads<XT, IDX>(a, item, sStage, 0, sOff, &carry, item + G < nitems ? item + G : -1);
+            stage_and_normalize<XT, IDX>(a, item, sStage, sA1, sStat, true);
             save_xhat(item);
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
             issue_gemm1();
-            if (item + G < nitems) issue_item_loads<XT>(a, item + G, sStage, 0, sOff, &carry, item + 2 * G < nitems ? item + 2 * G : -1);
+            if (item + G < nitems) issue_item_loads<XT, IDX>(a, item + G, sStage, 0, sOff, &carry, item + 2 * G < nitems ? item + 2 * G : -1);
         }
         for (; item < nitems; item += G, phase ^= 1) {
             mbar_wait(&bars[0], phase);
@@ -474,13 +483,13 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
             issue_gemm2();
             const int64_t nxt = item + G;
             if (nxt < nitems) {
-                stage_and_normalize<XT>(a, nxt, sStage, sA1, sStat, true);       // A1 is free: GEMM1(item) has completed
-                save_xhat(nxt);
+                stage_and_normalize<XT, IDX>(a, nxt, sStage, sA1, sStat, true);
+                save_xhat(nxt);       // A1 is free: GEMM1(item) has completed
                 fence_async_smem();
                 tc_fence_before_sync();
                 __syncthreads();
                 issue_gemm1();
-                if (nxt + G < nitems) issue_item_loads<XT>(a, nxt + G, sStage, 0, sOff, &carry, nxt + 2 * G < nitems ? nxt + 2 * G : -1);
+                if (nxt + G < nitems) issue_item_loads<XT, IDX>(a, nxt + G, sStage, 0, sOff, &carry, nxt + 2 * G < nitems ? nxt + 2 * G : -1);
             }
             mbar_wait(&bars[1], phase);
             tc_fence_after_sync();
@@ -489,7 +498,7 @@ __global__ void __launch_bounds__(NTH, 1) tc_front_fwd_kernel(ItemArgs a) {
         }
     } else {
         for (int64_t item = blockIdx.x; item < nitems; item += G, phase ^= 1) {
-            stage_and_normalize<XT>(a, item, sStage, sA1, sStat, false);
+            stage_and_normalize<XT, IDX>(a, item, sStage, sA1, sStat, false);
             save_xhat(item);
             fence_async_smem();
             tc_fence_before_sync();
