@@ -553,10 +553,19 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         atomicAdd(g.bsig + k, dpre1);
     }
     __syncthreads();
-    for (int idx = tid; idx < K * M; idx += NT) {          // dWmu, dWsig
-        const int k = idx / M, j = idx % M;
-        atomicAdd(g.Wmu + idx, dmupost[k] * yp[j]);
-        atomicAdd(g.Wsig + idx, dprepost[k] * yp[j]);
+    if ((M & 3) == 0) {                                     // dWmu, dWsig: one vector reduction per 4 portfolios
+        for (int i4 = tid; i4 < K * M / 4; i4 += NT) {
+            const int idx = 4 * i4, k = idx / M, j = idx % M;
+            const float a1 = dmupost[k], a2 = dprepost[k];
+            red_add_v4(g.Wmu + idx, a1 * yp[j], a1 * yp[j + 1], a1 * yp[j + 2], a1 * yp[j + 3]);
+            red_add_v4(g.Wsig + idx, a2 * yp[j], a2 * yp[j + 1], a2 * yp[j + 2], a2 * yp[j + 3]);
+        }
+    } else {
+        for (int idx = tid; idx < K * M; idx += NT) {
+            const int k = idx / M, j = idx % M;
+            atomicAdd(g.Wmu + idx, dmupost[k] * yp[j]);
+            atomicAdd(g.Wsig + idx, dprepost[k] * yp[j]);
+        }
     }
     for (int j = tid; j < M; j += NT) {                    // d y_p
         float v = 0.f;
@@ -616,9 +625,20 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         }
         dps[idx] = v;
     }
-    for (int idx = tid; idx < K * H * H; idx += NT) {      // dWv[k][j][h] = dctx[k][j] pooled[k][h]
-        const int k = idx / (H * H), r = idx % (H * H), j = r / H, h = r % H;
-        if (!bad[k]) atomicAdd(g.Wv + idx, tmpKH[k * H + j] * pooled[k * H + h]);
+    if ((H & 3) == 0) {                                     // dWv[k][j][h] = dctx[k][j] pooled[k][h], 4 h per reduction
+        for (int i4 = tid; i4 < K * H * H / 4; i4 += NT) {
+            const int idx = 4 * i4, k = idx / (H * H), r = idx % (H * H), j = r / H, h = r % H;
+            if (!bad[k]) {
+                const float dc = tmpKH[k * H + j];
+                const float* pl = pooled + k * H + h;
+                red_add_v4(g.Wv + idx, dc * pl[0], dc * pl[1], dc * pl[2], dc * pl[3]);
+            }
+        }
+    } else {
+        for (int idx = tid; idx < K * H * H; idx += NT) {
+            const int k = idx / (H * H), r = idx % (H * H), j = r / H, h = r % H;
+            if (!bad[k]) atomicAdd(g.Wv + idx, tmpKH[k * H + j] * pooled[k * H + h]);
+        }
     }
     __syncthreads();
     for (int k = tid; k < K; k += NT) {

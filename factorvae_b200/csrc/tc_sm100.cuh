@@ -58,11 +58,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// vector reduction into global memory (16-byte aligned address): a quarter of the atomic traffic of four scalar adds
-__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-
 // ---- fences ---------------------------------------------------------------------------------------
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
