@@ -108,3 +108,25 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu(cabi):
+    """Resident panel / optimizer / metric entry points reject bad arguments before touching the device."""
+    L = cabi.lib()
+    E_NULL, E_SHAPE, E_LIMIT, E_UNSUP = -1, -2, -3, -7
+    codes = {L.fvae_status_string(c).decode() for c in (E_NULL, E_SHAPE, E_LIMIT, E_UNSUP)}
+    assert len(codes) == 4
+    one = C.c_void_p(16)            # a non-null, 16-byte aligned dummy address (never dereferenced on these paths)
+    assert L.fvae_window_index(None, 4, 4, one, one, 8, 5, 2, 16, one, None, None, None) == E_NULL
+    assert L.fvae_window_index(one, 0, 4, one, one, 8, 5, 2, 16, one, None, None, None) == E_SHAPE
+    assert L.fvae_window_index(one, 4, 4, one, one, 8, 5, 3, 16, one, None, None, None) == E_UNSUP      # unknown fill mode
+    assert L.fvae_window_index(one, 4, 4, one, one, 8, 5, 2, 16, one, one, None, None) == E_NULL         # label without y
+    p = cabi.Panel(16, cabi.F32, 0, 158, None, 0)
+    assert L.fvae_gather_windows(C.byref(p), 8, 5, 158, one, cabi.F32, None) == E_NULL                  # no row index
+    p = cabi.Panel(16, cabi.F32, 0, 100, 16, 10)
+    assert L.fvae_gather_windows(C.byref(p), 8, 5, 158, one, cabi.F32, None) == E_SHAPE                 # pitch < C
+    assert L.fvae_adam_step(None, one, one, one, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) == E_NULL
+    assert L.fvae_adam_step(one, one, one, one, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None) == E_SHAPE   # steps are 1-based
+    assert L.fvae_adam_step(C.c_void_p(20), one, one, one, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) == E_SHAPE  # alignment
+    assert L.fvae_rank_ic(None, one, one, 3, 100, one, None) == E_NULL
+    assert L.fvae_rank_ic(one, one, one, 3, 5000, one, None) == E_LIMIT                                 # > 4096 stocks per date
