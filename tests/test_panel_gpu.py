@@ -80,3 +80,32 @@ def test_kernels_read_rows_through_the_index(prec, dtype, cuda_device):
         assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-4
     # gradients: identical inputs to every kernel; float atomics make the accumulation order free
     assert float((res[0][2] - res[1][2]).abs().max()) <= 1e-5 * float(res[0][2].abs().max())
+
+
+def test_batched_scoring_loop_is_chunking_invariant(cuda_device):
+    """generate_prediction_scores (utils.py:68-93 replacement): same scores whether 1, 3 or all dates go through one
+    fvae_predict call; frame indexed like the reference's; deterministic option returns mu_y."""
+    from factorvae_b200 import engine
+    from factorvae_b200.inference import generate_prediction_scores
+    from factorvae_b200.panel import ResidentPanel
+    import factorvae_b200 as fb
+    rng = np.random.default_rng(9)
+    D, I, Cf, T, H, K = 11, 140, 158, 5, 20, 20
+    dates = pd.date_range("2022-01-03", periods=D, freq="D")
+    rows = [(d, f"S{j:04d}") for d in dates for j in range(I) if rng.random() > 0.1]
+    df = pd.DataFrame(np.clip(rng.standard_normal((len(rows), Cf + 1)), -3, 3).astype(np.float32),
+                      index=pd.MultiIndex.from_tuples(rows, names=["datetime", "instrument"]))
+    rp = ResidentPanel.from_dataframe(df, Cf, cuda_device, start=dates[4])
+    torch.manual_seed(6)
+    m = fb.FactorVAE(fb.FeatureExtractor(Cf, H), fb.FactorEncoder(K, 128, H),
+                     fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, K)), fb.FactorPredictor(H, K))
+    L = engine.ParamLayout(Cf, H, K, 128)
+    flat = L.pack(m.state_dict(), cuda_device)
+    frames = [generate_prediction_scores(L, flat, rp, T, dates_per_call=n, seed=3)[0] for n in (1, 3, 64)]
+    assert list(frames[0].index.names) == ["datetime", "instrument"] and list(frames[0].columns) == ["score"]
+    assert frames[0].index.equals(df.sort_index().loc[dates[4]:].index)
+    for f in frames[1:]:
+        assert np.abs(f["score"].to_numpy() - frames[0]["score"].to_numpy()).max() <= 1e-4
+    det, extras = generate_prediction_scores(L, flat, rp, T, deterministic=True)
+    assert np.array_equal(det["score"].to_numpy(), extras["mu_y"])
+    assert np.isfinite(det["score"].to_numpy()).all() and (extras["sigma_y"] > 0).all()
