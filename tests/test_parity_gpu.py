@@ -388,3 +388,33 @@ def test_bf16_tc_heads_forward_modes_vs_fp32_kernels(mode, cuda_device):
         assert float((o16["mu_post"] - o32["mu_post"]).abs().max()) <= 1e-2
         assert _relmax(o16["sigma_post"], o32["sigma_post"]) <= 2e-2
         assert abs(float(o16["loss"]) - float(o32["loss"])) <= 2e-2 * abs(float(o32["loss"]))
+
+
+def test_bf16_tc_fe_more_tiles_than_resident_ctas(cuda_device):
+    """600 tiles on 592 (or fewer) resident GRU CTAs: the CTAs that take a second tile (bulk-copy ring refilled across the
+    tile boundary, h / dh state reset) must produce what a fresh launch over those rows produces, forward and backward."""
+    from factorvae_b200 import engine
+    import factorvae_b200 as fb
+    H, T = 20, 3
+    torch.manual_seed(13)
+    m = fb.FactorVAE(fb.FeatureExtractor(158, H), fb.FactorEncoder(20, 128, H),
+                     fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, 20)), fb.FactorPredictor(H, 20))
+    L = engine.ParamLayout(158, H, 20, 128)
+    flat = L.pack(m.state_dict(), cuda_device)
+    S = 600 * 128 + 37
+    g = torch.Generator(device=cuda_device).manual_seed(2)
+    x = torch.randn(S, T, 158, device=cuda_device, generator=g).clamp_(-3, 3).to(torch.bfloat16)
+    de = torch.randn(S, H, device=cuda_device, generator=g)
+    e_all, st_all = engine.fe_forward(L, flat, x, "bf16")
+    e_all = e_all.clone()
+    g_all = engine.fe_backward(L, st_all, de).clone()
+    lo = 580 * 128                                    # the tail, re-run alone: every CTA then owns exactly one tile
+    e_tail, st_tail = engine.fe_forward(L, flat, x[lo:], "bf16")
+    assert torch.equal(e_all[lo:], e_tail)
+    # gradients: whole = head part + tail part (atomics: compare with a tolerance)
+    g_tail = engine.fe_backward(L, st_tail, de[lo:]).clone()
+    e_head, st_head = engine.fe_forward(L, flat, x[:lo], "bf16")
+    assert torch.equal(e_all[:lo], e_head)
+    g_head = engine.fe_backward(L, st_head, de[:lo]).clone()
+    ref = g_head + g_tail
+    assert float((g_all - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
