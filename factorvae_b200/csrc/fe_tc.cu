@@ -687,8 +687,8 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 512>, gru_threads(kNB), 512, smem, st, g)); }
         if (rc != 0) return rc;
     }
-    cudaError_t ce = cudaMemsetAsync(ws.q, 0, size_t(256) * CP * 4, st);
-    if (ce == cudaSuccess) ce = cudaMemsetAsync(ws.dwih, 0, size_t(256) * CP * 4, st);
+    // q and dwih are adjacent in the workspace (carve_tc): one memset node
+    cudaError_t ce = cudaMemsetAsync(ws.q, 0, size_t(reinterpret_cast<char*>(ws.dwih) - reinterpret_cast<char*>(ws.q)) + size_t(256) * CP * 4, st);
     if (ce != cudaSuccess) return int(ce);
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);

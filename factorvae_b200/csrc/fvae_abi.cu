@@ -263,8 +263,8 @@ int fvae_elbo_backward(const fvae_shape* shape, const fvae_panel* x, const float
     const FeDims fd{shape->S, shape->T, shape->C, shape->H};
     cudaError_t ce = cudaMemsetAsync(grad, 0, size_t(L.off[FVAE_P_NUM_SECTIONS]) * sizeof(float), st);
     if (ce != cudaSuccess) return int(ce);
-    if ((ce = cudaMemsetAsync(W.sv.dG, 0, size_t(shape->K) * shape->H * sizeof(float), st)) != cudaSuccess) return int(ce);
-    if ((ce = cudaMemsetAsync(W.sv.dc, 0, size_t(shape->K) * sizeof(float), st)) != cudaSuccess) return int(ce);
+    // dG and dc are adjacent in the workspace (carve): one memset node
+    if ((ce = cudaMemsetAsync(W.sv.dG, 0, size_t(reinterpret_cast<char*>(W.sv.dc) - reinterpret_cast<char*>(W.sv.dG)) + size_t(shape->K) * sizeof(float), st)) != cudaSuccess) return int(ce);
     if ((rc = heads_backward(a, hg, W.dE, st)) != 0) return rc;
     if ((rc = heads_post(a, hg, st)) != 0) return rc;
     if ((rc = fe_backward_any(fd, *x, fw, fg, precision, W.dE, W.fe_ws, st)) != 0) return rc;
