@@ -200,7 +200,7 @@ __device__ __forceinline__ void expand_compact(const float (&a)[8], const float 
 constexpr int gru_min_ctas(int NB8) { return NB8 <= 3 ? 4 : (NB8 == 4 ? 2 : 1); }
 
 template <int NB8, uint32_t TCOLS>
-__global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_fwd_kernel(GruArgs a) {
+__global__ void __launch_bounds__(gru_threads(NB8), (TCOLS == 64 && NB8 <= 3) ? 5 : gru_min_ctas(NB8)) tc_gru_fwd_kernel(GruArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NTHR = gru_threads(NB8), BPT = gru_bpt(NB8);
     const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TM - 1), blk0 = (tid >> 7) * BPT;
@@ -649,7 +649,7 @@ int launch_gru(KernelT k, int threads, uint32_t tmem_cols, size_t smem, cudaStre
     const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
     int occ = 2048 / threads;
     const int by_regs = 65536 / (regs_per_warp * (threads / 32));
-    const int by_smem = int(size_t(227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+    const int by_smem = int(size_t(228 * 1024) / (smem + fa.sharedSizeBytes + 1024));      // 228 KB per SM, 1 KB reserved per CTA
     const int by_tmem = int(512u / tmem_cols);
     if (occ > by_regs) occ = by_regs;
     if (occ > by_smem) occ = by_smem;
@@ -731,9 +731,11 @@ int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, 
     size_t smem = size_t(HP / 8) * NC * 16 + size_t(HP / 8) * TILE_CH + HP * 4 + 64;
     {   // gate pre-activation ring: only while four CTAs still fit one SM
         const size_t with_ring = smem + 256 + 2 * size_t(NC / 8) * TILE_CH;
-        if (NC <= 128 && with_ring <= 56 * 1024) { g.gi_ring = 1; smem = with_ring; }
+        const size_t ring_cap = NC <= 64 ? 45600 : 56 * 1024;           // five CTAs per SM with a 64-column accumulator (228 KB / 5 - 1 KB)
+        if (NC <= 128 && with_ring <= ring_cap) { g.gi_ring = 1; smem = with_ring; }
     }
-    if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 128>, gru_threads(kNB), 128, smem, st, g)); }
+    if (NC <= 64) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 64>, gru_threads(kNB), 64, smem, st, g)); }
+    else if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 128>, gru_threads(kNB), 128, smem, st, g)); }
     else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 256>, gru_threads(kNB), 256, smem, st, g)); }
     return rc;
 }
