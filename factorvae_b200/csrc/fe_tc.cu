@@ -46,7 +46,11 @@ __host__ __device__ inline int nb8_of(int H) { return (H + 7) / 8; }
 // finds the three gates of its units in adjacent chunks.  When the last block holds at most 4 units it is COMPACT:
 // [r4 z4 | n4 0000] = two chunks (H = 20: 24 + 24 + 16 = 64 columns instead of 80 -> 20 % less GI / dGI traffic and a
 // 64-column TMEM accumulator for the forward GRU).
-__host__ __device__ inline bool gate_compact(int H) { const int r = H & 7; return r >= 1 && r <= 4; }
+// ... used only where it actually shrinks the padded column count (H = 20: 64 < 80; H = 60: 192 either way -> plain blocks)
+__host__ __device__ inline bool gate_compact(int H) {
+    const int r = H & 7, nb = nb8_of(H);
+    return r >= 1 && r <= 4 && pad16(24 * (nb - 1) + 16) < pad16(24 * nb);
+}
 __host__ __device__ inline int nc_of(int H) {                                     // gate columns (permuted, padded)
     return gate_compact(H) ? pad16(24 * (nb8_of(H) - 1) + 16) : pad16(24 * nb8_of(H));
 }
@@ -199,7 +203,8 @@ __device__ __forceinline__ void expand_compact(const float (&a)[8], const float 
 }
 constexpr int gru_min_ctas(int NB8) { return NB8 <= 3 ? 4 : (NB8 == 4 ? 2 : 1); }
 
-template <int NB8, uint32_t TCOLS>
+// CMP: the last gate block is compact (gate_compact(H)); a template parameter so the plain-layout kernels carry none of its code
+template <int NB8, uint32_t TCOLS, bool CMP>
 __global__ void __launch_bounds__(gru_threads(NB8), (TCOLS == 64 && NB8 <= 3) ? 5 : gru_min_ctas(NB8)) tc_gru_fwd_kernel(GruArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NTHR = gru_threads(NB8), BPT = gru_bpt(NB8);
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(gru_threads(NB8), (TCOLS == 64 && NB8 <= 3) ? 
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = uint32_t(warp & 3) * 32u;
     uint32_t phase = 0;
-    const bool cmp = gate_compact(H);                              // the last block is [r4 z4 | n4]: two chunks
+    constexpr bool cmp = CMP;                                      // the last block is [r4 z4 | n4]: two chunks
     const int nq = (cmp && blk0 + BPT == NB8) ? 3 * BPT - 1 : 3 * BPT;   // chunks of the GI tile that are mine
     if (ring && tid == 0) { if (total_q > 0) fill(0); if (total_q > 1) fill(1); }
     int64_t q = 0;
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(gru_threads(NB8), (TCOLS == 64 && NB8 <= 3) ? 
 }
 
 // ---- K3: GRU backward (BPTT) -------------------------------------------------------------------------------------
-template <int NB8, uint32_t TCOLS>
+template <int NB8, uint32_t TCOLS, bool CMP>
 __global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bwd_kernel(GruArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NTHR = gru_threads(NB8), BPT = gru_bpt(NB8), NTB = NB8 / BPT;
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bw
     const uint32_t lane_base = uint32_t(warp & 3) * 32u;
     uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
     bool dw_pending = false, dw_started = false;
-    const bool cmp = gate_compact(H);                              // the last block is [r4 z4 | n4]: two chunks
+    constexpr bool cmp = CMP;                                      // the last block is [r4 z4 | n4]: two chunks
     const int nq = (cmp && blk0 + BPT == NB8) ? 3 * BPT - 1 : 3 * BPT;
     // constant chunk of the h operand tile: zeros, with the ones column where H falls into chunk b
     auto const_chunk = [&](int b) {
@@ -734,9 +739,9 @@ int fe_tc_forward(const FeDims& d, const fvae_panel& x, const FeW& w, float* e, 
         const size_t ring_cap = NC <= 64 ? 45600 : 56 * 1024;           // five CTAs per SM with a 64-column accumulator (228 KB / 5 - 1 KB)
         if (NC <= 128 && with_ring <= ring_cap) { g.gi_ring = 1; smem = with_ring; }
     }
-    if (NC <= 64) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 64>, gru_threads(kNB), 64, smem, st, g)); }
-    else if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 128>, gru_threads(kNB), 128, smem, st, g)); }
-    else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_fwd_kernel<kNB, 256>, gru_threads(kNB), 256, smem, st, g)); }
+    if (NC <= 64) { FVAE_DISPATCH_NB8(NB, rc = (gate_compact(d.H) ? launch_gru(tc_gru_fwd_kernel<kNB, 64, true>, gru_threads(kNB), 64, smem, st, g) : launch_gru(tc_gru_fwd_kernel<kNB, 64, false>, gru_threads(kNB), 64, smem, st, g))); }
+    else if (NC <= 128) { FVAE_DISPATCH_NB8(NB, rc = (gate_compact(d.H) ? launch_gru(tc_gru_fwd_kernel<kNB, 128, true>, gru_threads(kNB), 128, smem, st, g) : launch_gru(tc_gru_fwd_kernel<kNB, 128, false>, gru_threads(kNB), 128, smem, st, g))); }
+    else { FVAE_DISPATCH_NB8(NB, rc = (gate_compact(d.H) ? launch_gru(tc_gru_fwd_kernel<kNB, 256, true>, gru_threads(kNB), 256, smem, st, g) : launch_gru(tc_gru_fwd_kernel<kNB, 256, false>, gru_threads(kNB), 256, smem, st, g))); }
     return rc;
 }
 
@@ -751,9 +756,9 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         const int MB = NC > 128 ? 2 : 1;
         const size_t smem = size_t(HP / 8) * NC * 16 + size_t(NC / 8) * HP * 16 + size_t(HP / 8) * TILE_CH + size_t(16 * MB) * TILE_CH + HP * 4 + 64;
         const uint32_t cols = uint32_t(NC + MB * HP);
-        if (cols <= 128) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 128>, gru_threads(kNB), 128, smem, st, g)); }
-        else if (cols <= 256) { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 256>, gru_threads(kNB), 256, smem, st, g)); }
-        else { FVAE_DISPATCH_NB8(NB, rc = launch_gru(tc_gru_bwd_kernel<kNB, 512>, gru_threads(kNB), 512, smem, st, g)); }
+        if (cols <= 128) { FVAE_DISPATCH_NB8(NB, rc = (gate_compact(d.H) ? launch_gru(tc_gru_bwd_kernel<kNB, 128, true>, gru_threads(kNB), 128, smem, st, g) : launch_gru(tc_gru_bwd_kernel<kNB, 128, false>, gru_threads(kNB), 128, smem, st, g))); }
+        else if (cols <= 256) { FVAE_DISPATCH_NB8(NB, rc = (gate_compact(d.H) ? launch_gru(tc_gru_bwd_kernel<kNB, 256, true>, gru_threads(kNB), 256, smem, st, g) : launch_gru(tc_gru_bwd_kernel<kNB, 256, false>, gru_threads(kNB), 256, smem, st, g))); }
+        else { FVAE_DISPATCH_NB8(NB, rc = (gate_compact(d.H) ? launch_gru(tc_gru_bwd_kernel<kNB, 512, true>, gru_threads(kNB), 512, smem, st, g) : launch_gru(tc_gru_bwd_kernel<kNB, 512, false>, gru_threads(kNB), 512, smem, st, g))); }
         if (rc != 0) return rc;
     }
     // q and dwih are adjacent in the workspace (carve_tc): one memset node
