@@ -160,7 +160,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a stuck rendezvous / collective must end as an error within minutes, never as a hung box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     B, N, T, H, K, M = (wl[k] for k in "BNTHKM")
     S = B * N
     precision = args.precision
