@@ -162,7 +162,7 @@ def main():
     if world > 1:
         import datetime
         # a stuck rendezvous / collective must end as an error within minutes, never as a hung box
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     B, N, T, H, K, M = (wl[k] for k in "BNTHKM")
     S = B * N
     precision = args.precision
@@ -200,7 +200,18 @@ def main():
     t_warm = time.perf_counter()
     for _ in range(args.warmup):
         one_step()
-    while time.perf_counter() - t_warm < 0.5:       # keep the GPU under load long enough for a few clock samples
+    # keep the GPU under load for ~0.5 s so the clock sampler sees a few samples.  The number of extra steps must be the
+    # SAME on every rank (each step carries an all-reduce): agree on it with one collective instead of a per-rank clock.
+    torch.cuda.synchronize()
+    t_probe = time.perf_counter()
+    for _ in range(10):                                            # fixed count: identical on every rank
+        one_step()
+    torch.cuda.synchronize()
+    per_step = max((time.perf_counter() - t_probe) / 10.0, 1e-5)
+    extra = torch.tensor([int(min(5000, max(0.0, 0.5 - (time.perf_counter() - t_warm)) / per_step))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(extra, op=dist.ReduceOp.MAX)
+    for _ in range(int(extra.item())):
         one_step()
     barrier()
     l0 = lib.fvae_debug_launch_count()
