@@ -130,3 +130,18 @@ def test_new_entry_points_validate_arguments_without_a_gpu(cabi):
     assert L.fvae_adam_step(C.c_void_p(20), one, one, one, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) == E_SHAPE  # alignment
     assert L.fvae_rank_ic(None, one, one, 3, 100, one, None) == E_NULL
     assert L.fvae_rank_ic(one, one, one, 3, 5000, one, None) == E_LIMIT                                 # > 4096 stocks per date
+
+
+def test_next_row_modules_have_no_cpu_fallback(cabi):
+    """Resident panel, fused optimizer and metric fail loudly on CPU tensors / devices instead of falling back."""
+    import numpy as np
+    from factorvae_b200.metrics import rank_ic
+    from factorvae_b200.optim import FlatAdam
+    from factorvae_b200.panel import PanelIndex, ResidentPanel
+    with pytest.raises(RuntimeError):
+        FlatAdam(torch.zeros(16))
+    with pytest.raises(RuntimeError):
+        rank_ic(torch.zeros(4), torch.zeros(4), torch.tensor([0, 4], dtype=torch.int32))
+    idx = PanelIndex(np.zeros((2, 2), np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32), np.array([0, 1]), 4)
+    with pytest.raises(RuntimeError):
+        ResidentPanel(np.zeros((4, 3), np.float32), idx, 2, "cpu")
