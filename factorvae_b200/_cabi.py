@@ -13,7 +13,7 @@ F32, BF16 = 0, 1
 PREC_FP32, PREC_BF16_TC = 0, 1
 FLAG_TRAIN, FLAG_PHILOX = 1, 2
 FILL_NONE, FILL_FFILL, FILL_FFILL_BFILL = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SECTIONS = [
     "LN_W", "LN_B", "W1", "B1", "WIH", "WHH", "BIH", "BHH",
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
     L.fvae_fe_backward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i32, vp, vp, vp, i64, vp]
     L.fvae_debug_front_forward.restype = C.c_int
     L.fvae_debug_front_forward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i64, vp]
+    L.fvae_debug_noise.restype = C.c_int
+    L.fvae_debug_noise.argtypes = [C.c_uint64, C.c_uint64, i64, i64, i32, vp, vp, vp]
     L.fvae_workspace_latent.restype = vp
     L.fvae_workspace_latent.argtypes = [C.POINTER(Shape), i32, vp]
     L.fvae_window_index.restype = C.c_int
@@ -100,7 +102,7 @@ def lib() -> C.CDLL:
     return L
 
 
-EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_debug_front_forward", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
+EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_debug_front_forward", "fvae_debug_noise", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
            "fvae_elbo_forward", "fvae_elbo_backward", "fvae_predict", "fvae_fe_forward", "fvae_fe_backward",
            "fvae_workspace_latent", "fvae_window_index", "fvae_gather_windows", "fvae_adam_step", "fvae_rank_ic"]
 

@@ -46,6 +46,28 @@ class DateShardedStep:
     def loss(self) -> torch.Tensor:
         return self.gradbuf[self.layout.total: self.layout.total + 1]
 
+    def _local(self, x, y, date_ptr, *, unit_base=0, train=True, eps=None, keep_mask=None):
+        """Forward + backward over the given dates into self.gradbuf (gradient of the MEAN over these dates, loss in the
+        tail); no collective."""
+        noise = dict(eps=eps, keep_mask=keep_mask) if eps is not None else dict(philox=(self.seed, self.step_index, unit_base))
+        out, st = engine.elbo_forward(self.layout, self.flat, x, y, date_ptr, train=train, precision=self.precision,
+                                      workspace=self.workspace, loss_out=self.loss, **noise)
+        self.workspace = st.workspace
+        engine.elbo_backward(self.layout, st, grad=self.grad)
+        return out, st
+
+    def _reduce(self, buf: torch.Tensor, local_weight: float) -> None:
+        """The single gradient exchange of the step: buf <- sum over ranks of local_weight * buf (loss in the tail)."""
+        if self.world > 1:
+            if abs(local_weight * self.world - 1.0) < 1e-12 and dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                if local_weight != 1.0:
+                    buf.mul_(local_weight)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        elif local_weight != 1.0:
+            buf.mul_(local_weight)
+
     def step(self, x: torch.Tensor, y: torch.Tensor, date_ptr: torch.Tensor, *, global_dates: Optional[int] = None,
              unit_base: int = 0, train: bool = True, eps: Optional[torch.Tensor] = None,
              keep_mask: Optional[torch.Tensor] = None):
@@ -57,20 +79,30 @@ class DateShardedStep:
         self.step_index += 1
         B_local = date_ptr.numel() - 1
         B_global = global_dates if global_dates is not None else B_local * self.world
-        noise = dict(eps=eps, keep_mask=keep_mask) if eps is not None else dict(philox=(self.seed, self.step_index, unit_base))
-        out, st = engine.elbo_forward(self.layout, self.flat, x, y, date_ptr, train=train, precision=self.precision,
-                                      workspace=self.workspace, loss_out=self.loss, **noise)
-        self.workspace = st.workspace
-        engine.elbo_backward(self.layout, st, grad=self.grad)
-        if self.world > 1:
-            if B_local * self.world == B_global and dist.get_backend(self.group) == "nccl":
-                dist.all_reduce(self.gradbuf, op=dist.ReduceOp.AVG, group=self.group)
-            else:
-                self.gradbuf.mul_(float(B_local) / float(B_global))
-                dist.all_reduce(self.gradbuf, op=dist.ReduceOp.SUM, group=self.group)
-        elif B_local != B_global:
-            self.gradbuf.mul_(float(B_local) / float(B_global))
+        out, st = self._local(x, y, date_ptr, unit_base=unit_base, train=train, eps=eps, keep_mask=keep_mask)
+        self._reduce(self.gradbuf, float(B_local) / float(B_global))
         return out, st
+
+    def step_accumulate(self, micro_batches, *, global_dates: int, train: bool = True):
+        """One step over this rank's dates processed as several micro-batches (a per-GPU share too large for one workspace:
+        BASELINE.json configs[3..4] on few GPUs).  micro_batches: iterable of (x, y, date_ptr, unit_base).  Gradients are
+        accumulated locally with weight B_micro / B_global, then exchanged ONCE.  The result equals step() over the
+        concatenated dates (noise is keyed by the global unit id)."""
+        self.step_index += 1
+        acc = getattr(self, "_acc", None)
+        if acc is None:
+            acc = self._acc = torch.zeros_like(self.gradbuf)
+        first = True
+        for x, y, date_ptr, unit_base in micro_batches:
+            self._local(x, y, date_ptr, unit_base=unit_base, train=train)
+            w = float(date_ptr.numel() - 1) / float(global_dates)
+            if first:
+                torch.mul(self.gradbuf, w, out=acc)
+                first = False
+            else:
+                acc.add_(self.gradbuf, alpha=w)
+        self._reduce(acc, 1.0)
+        self.gradbuf.copy_(acc)
 
     def step_from_host(self, x_host: torch.Tensor, y_host: torch.Tensor, date_ptr_host: torch.Tensor, **kw):
         """End-to-end entry: pinned HOST buffers in, loss (a Python float) out -- the H2D copy of the

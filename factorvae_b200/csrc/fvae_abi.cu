@@ -68,7 +68,9 @@ int check_shape(const fvae_shape* s, int precision) {
     if (!s) return FVAE_ERR_NULL;
     if (s->S <= 0 || s->B <= 0 || s->T <= 0 || s->C <= 0 || s->H <= 0 || s->K <= 0 || s->M <= 0 || s->B > s->S)
         return FVAE_ERR_SHAPE;
-    if (s->C > kMaxC || s->H > kMaxH) return FVAE_ERR_LIMIT;
+    // K, M bounds: the per-date phases of the heads kernels deal one factor / portfolio per thread of a 256-thread CTA
+    // (heads.cu: NSC = NT / K would be 0 for K > 256 and the posterior-path column sums would silently be zero)
+    if (s->C > kMaxC || s->H > kMaxH || s->K > 256 || s->M > 1024) return FVAE_ERR_LIMIT;
     if (precision != FVAE_PREC_FP32 && precision != FVAE_PREC_BF16_TC) return FVAE_ERR_DTYPE;
     if (precision == FVAE_PREC_BF16_TC) {
         const FeDims fd{s->S, s->T, s->C, s->H};
@@ -199,7 +201,7 @@ const char* fvae_status_string(int status) {
         case FVAE_OK: return "ok";
         case FVAE_ERR_NULL: return "a required pointer is NULL";
         case FVAE_ERR_SHAPE: return "invalid shape or pitch";
-        case FVAE_ERR_LIMIT: return "outside the supported range (C<=192, H<=64, shared memory)";
+        case FVAE_ERR_LIMIT: return "outside the supported range (C<=192, H<=64, K<=256, M<=1024, shared memory)";
         case FVAE_ERR_DTYPE: return "unknown dtype or precision";
         case FVAE_ERR_WORKSPACE: return "workspace too small or not 256-byte aligned";
         case FVAE_ERR_NO_DEVICE: return "no CUDA device of the required architecture (sm_100a)";

@@ -14,7 +14,9 @@ namespace {
 constexpr int kRankMaxN = 4096;       // stocks per date held in shared memory
 constexpr int kRankThreads = 256;
 
-// sort (key, idx) ascending by key; n2 = power of two >= n, padded with +inf
+// sort (key, idx) ascending by the TOTAL order (key, idx); n2 = power of two >= n, padded with (+inf, idx >= n).  The
+// tie-break on idx matters: a bitonic network is not stable, and with a plain key compare the padding slots could land in
+// front of a real +inf (or NaN -> +inf) element, i.e. at a sorted position p < n, and be ranked as if they were stocks.
 __device__ void bitonic_sort(float* key, int* idx, int n2) {
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -23,7 +25,8 @@ __device__ void bitonic_sort(float* key, int* idx, int n2) {
                 if (l > i) {
                     const bool up = (i & k) == 0;
                     const float a = key[i], b = key[l];
-                    if ((a > b) == up) { key[i] = b; key[l] = a; const int t = idx[i]; idx[i] = idx[l]; idx[l] = t; }
+                    const bool gt = a > b || (a == b && idx[i] > idx[l]);
+                    if (gt == up) { key[i] = b; key[l] = a; const int t = idx[i]; idx[i] = idx[l]; idx[l] = t; }
                 }
             }
             __syncthreads();
@@ -40,7 +43,7 @@ __device__ void average_ranks(const float* __restrict__ v, int n, int n2, float*
     }
     __syncthreads();
     bitonic_sort(key, idx, n2);
-    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {     // positions [0, n) hold exactly the real entries (total order)
         const float x = key[p];
         int lo = p, hi = p;
         while (lo > 0 && key[lo - 1] == x) --lo;

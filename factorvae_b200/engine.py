@@ -94,6 +94,7 @@ class StepState:
     precision: int
     tensors: Dict[str, torch.Tensor]   # keeps every buffer alive
     workspace: torch.Tensor
+    flat_version: Optional[int] = None   # flat._version at forward: backward refuses parameters modified in between
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -167,8 +168,15 @@ def single_date_ptr(N: int, device) -> torch.Tensor:
     return t
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device) -> C.c_void_p:
+    """The current stream OF THE DEVICE the buffers live on (not of the current device)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _on(device):
+    """Every ABI call runs with the buffers' device current: kernel attributes, launches and the stream all belong to it
+    (a model on cuda:1 while cuda:0 is current must not launch on device 0 with device-1 pointers)."""
+    return torch.cuda.device(device)
 
 
 def uniform_date_ptr(B: int, N: int, device) -> torch.Tensor:
@@ -232,9 +240,12 @@ def elbo_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, y: Op
         _cabi.check(int(need), "fvae_workspace_bytes")
     if workspace is None or workspace.numel() < need or workspace.device != dev:
         workspace = torch.empty(int(need), dtype=torch.uint8, device=dev)
+    if flat.device != dev:
+        raise RuntimeError(f"parameters live on {flat.device}, the batch on {dev}")
     if predict:
-        rc = L.fvae_predict(C.byref(shape), C.byref(panel), date_ptr.data_ptr(), flat.data_ptr(), C.byref(noise), flags,
-                            prec, C.byref(outs), workspace.data_ptr(), workspace.numel(), _stream())
+        with _on(dev):
+            rc = L.fvae_predict(C.byref(shape), C.byref(panel), date_ptr.data_ptr(), flat.data_ptr(), C.byref(noise), flags,
+                                prec, C.byref(outs), workspace.data_ptr(), workspace.numel(), _stream(dev))
         _cabi.check(rc, "fvae_predict")
     else:
         _require_cuda(y, "returns")
@@ -242,12 +253,13 @@ def elbo_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, y: Op
         if y.numel() != S:
             raise ValueError("returns must have one entry per stock")
         keep["y"] = y
-        rc = L.fvae_elbo_forward(C.byref(shape), C.byref(panel), y.data_ptr(), date_ptr.data_ptr(), flat.data_ptr(),
-                                 C.byref(noise), flags, prec, C.byref(outs), workspace.data_ptr(), workspace.numel(),
-                                 _stream())
+        with _on(dev):
+            rc = L.fvae_elbo_forward(C.byref(shape), C.byref(panel), y.data_ptr(), date_ptr.data_ptr(), flat.data_ptr(),
+                                     C.byref(noise), flags, prec, C.byref(outs), workspace.data_ptr(), workspace.numel(),
+                                     _stream(dev))
         _cabi.check(rc, "fvae_elbo_forward")
     keep.update(out)
-    st = StepState(shape, panel, noise, outs, flags, prec, keep, workspace)
+    st = StepState(shape, panel, noise, outs, flags, prec, keep, workspace, flat._version)
     return out, st
 
 
@@ -257,18 +269,36 @@ def elbo_backward(layout: ParamLayout, st: StepState, grad: Optional[torch.Tenso
     t = st.tensors
     if grad is None:
         grad = torch.empty(layout.total, dtype=torch.float32, device=t["flat"].device)
-    rc = L.fvae_elbo_backward(C.byref(st.shape), C.byref(st.panel), t["y"].data_ptr(), t["date_ptr"].data_ptr(),
-                              t["flat"].data_ptr(), C.byref(st.noise), st.flags, st.precision, C.byref(st.outs),
-                              grad.data_ptr(), st.workspace.data_ptr(), st.workspace.numel(), _stream())
+    dev = t["flat"].device
+    if st.flat_version is not None and t["flat"]._version != st.flat_version:
+        raise RuntimeError("the parameters were modified in place between forward and backward (optimizer.step() / "
+                           "load_state_dict before loss.backward()): the saved activations no longer match them")
+    with _on(dev):
+        rc = L.fvae_elbo_backward(C.byref(st.shape), C.byref(st.panel), t["y"].data_ptr(), t["date_ptr"].data_ptr(),
+                                  t["flat"].data_ptr(), C.byref(st.noise), st.flags, st.precision, C.byref(st.outs),
+                                  grad.data_ptr(), st.workspace.data_ptr(), st.workspace.numel(), _stream(dev))
     _cabi.check(rc, "fvae_elbo_backward")
     return grad
 
 
 def rerun_front_forward(st: StepState) -> None:
     """Diagnostics: launch only the dominant tensor-core kernel again on the state of a bf16 forward (bench.py)."""
-    rc = _cabi.lib().fvae_debug_front_forward(C.byref(st.shape), C.byref(st.panel), st.workspace.data_ptr(),
-                                              st.workspace.numel(), _stream())
+    dev = st.workspace.device
+    with _on(dev):
+        rc = _cabi.lib().fvae_debug_front_forward(C.byref(st.shape), C.byref(st.panel), st.workspace.data_ptr(),
+                                                  st.workspace.numel(), _stream(dev))
     _cabi.check(rc, "fvae_debug_front_forward")
+
+
+def philox_noise(seed: int, step: int, unit_base: int, S: int, K: int, device):
+    """Diagnostics: (eps (S,), keep_mask (S, K) uint8) a philox=(seed, step, unit_base) step draws (fvae_debug_noise)."""
+    eps = torch.empty(S, dtype=torch.float32, device=device)
+    keep = torch.empty(S, K, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        rc = _cabi.lib().fvae_debug_noise(int(seed) & (2 ** 64 - 1), int(step), int(unit_base), S, K, eps.data_ptr(),
+                                          keep.data_ptr(), C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    _cabi.check(rc, "fvae_debug_noise")
+    return eps, keep
 
 
 def latent(st: StepState) -> torch.Tensor:
@@ -293,8 +323,9 @@ def fe_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, precisi
         _cabi.check(int(need), "fvae_workspace_bytes")
     ws = torch.empty(int(need), dtype=torch.uint8, device=x.device)
     e = torch.empty(S, layout.H, dtype=torch.float32, device=x.device)
-    rc = L.fvae_fe_forward(C.byref(shape), C.byref(panel), flat.data_ptr(), prec, e.data_ptr(), ws.data_ptr(), ws.numel(),
-                           _stream())
+    with _on(x.device):
+        rc = L.fvae_fe_forward(C.byref(shape), C.byref(panel), flat.data_ptr(), prec, e.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _stream(x.device))
     _cabi.check(rc, "fvae_fe_forward")
     return e, (shape, panel, prec, ws, x, flat)
 
@@ -304,7 +335,8 @@ def fe_backward(layout: ParamLayout, saved, de: torch.Tensor) -> torch.Tensor:
     shape, panel, prec, ws, x, flat = saved
     de = de.to(dtype=torch.float32).contiguous()
     grad = torch.zeros(layout.total, dtype=torch.float32, device=x.device)
-    rc = L.fvae_fe_backward(C.byref(shape), C.byref(panel), flat.data_ptr(), prec, de.data_ptr(), grad.data_ptr(),
-                            ws.data_ptr(), ws.numel(), _stream())
+    with _on(x.device):
+        rc = L.fvae_fe_backward(C.byref(shape), C.byref(panel), flat.data_ptr(), prec, de.data_ptr(), grad.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream(x.device))
     _cabi.check(rc, "fvae_fe_backward")
     return grad

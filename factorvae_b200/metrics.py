@@ -6,7 +6,7 @@ from typing import Tuple
 import torch
 
 from . import _cabi
-from .engine import _stream
+from .engine import _on, _stream
 
 
 def rank_ic(pred: torch.Tensor, label: torch.Tensor, date_ptr: torch.Tensor) -> Tuple[torch.Tensor, float, float]:
@@ -22,7 +22,9 @@ def rank_ic(pred: torch.Tensor, label: torch.Tensor, date_ptr: torch.Tensor) -> 
     counts = (date_ptr[1:] - date_ptr[:-1])
     nmax = int(counts.max().item()) if B > 0 else 0
     ric = torch.empty(B, dtype=torch.float32, device=pred.device)
-    rc = _cabi.lib().fvae_rank_ic(pred.data_ptr(), label.data_ptr(), date_ptr.data_ptr(), B, max(nmax, 1), ric.data_ptr(), _stream())
+    with _on(pred.device):
+        rc = _cabi.lib().fvae_rank_ic(pred.data_ptr(), label.data_ptr(), date_ptr.data_ptr(), B, max(nmax, 1), ric.data_ptr(),
+                                      _stream(pred.device))
     _cabi.check(rc, "fvae_rank_ic")
     r64 = ric.double()
     mean = float(r64.mean().item()) if B else float("nan")

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .engine import IndexedWindows, _stream
+from .engine import IndexedWindows, _on, _stream
 
 FILL = {"none": _cabi.FILL_NONE, "ffill": _cabi.FILL_FFILL, "ffill+bfill": _cabi.FILL_FFILL_BFILL}
 
@@ -125,6 +125,18 @@ class ResidentPanel:
         idx = PanelIndex.from_dataframe(df, start, end)
         return ResidentPanel(df.sort_index().to_numpy(dtype=np.float32), idx, num_features, device, dtype)
 
+    def upload_rows(self, first_row: int, rows_host: torch.Tensor, labels_host: Optional[torch.Tensor] = None) -> None:
+        """Overwrite table rows [first_row, first_row + n) from a pinned HOST buffer (n, pitch) of the table's dtype (and
+        their labels (n,) fp32): the streaming form of the resident panel -- every (date, instrument) row crosses PCIe
+        exactly once, when its date enters the look-back horizon, instead of T times inside T overlapping windows
+        (dataset.py:169-181 materialises every window on the host).  Asynchronous on the current stream."""
+        n = rows_host.shape[0]
+        if rows_host.dtype != self.table.dtype or rows_host.shape[1] != self.table.shape[1] or first_row < 0 or first_row + n > self.index.num_rows:
+            raise ValueError("rows_host must be (n, pitch) in the table's dtype and fit the table")
+        self.table[first_row:first_row + n].copy_(rows_host, non_blocking=True)
+        if labels_host is not None:
+            self.label[first_row:first_row + n].copy_(labels_host, non_blocking=True)
+
     @property
     def num_batches(self) -> int:
         return len(self.index.date_ptr) - 1
@@ -146,8 +158,10 @@ class ResidentPanel:
         row_index = torch.empty(S, T, dtype=torch.int32, device=self.device)
         y = torch.empty(S, dtype=torch.float32, device=self.device)
         D, I = self.index.idx_mat.shape
-        rc = _cabi.lib().fvae_window_index(self.idx_mat.data_ptr(), D, I, sd.data_ptr(), sj.data_ptr(), S, T, FILL[fill],
-                                           self.index.nan_row, row_index.data_ptr(), self.label.data_ptr(), y.data_ptr(), _stream())
+        with _on(self.device):
+            rc = _cabi.lib().fvae_window_index(self.idx_mat.data_ptr(), D, I, sd.data_ptr(), sj.data_ptr(), S, T, FILL[fill],
+                                               self.index.nan_row, row_index.data_ptr(), self.label.data_ptr(), y.data_ptr(),
+                                               _stream(self.device))
         _cabi.check(rc, "fvae_window_index")
         date_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(self.device)
         return IndexedWindows(self.table, row_index, self.C), y, date_ptr
@@ -158,7 +172,8 @@ class ResidentPanel:
         out = torch.empty(S, T, Cf, dtype=dtype, device=self.device)
         from .engine import _panel
         _, panel = _panel(xw)
-        rc = _cabi.lib().fvae_gather_windows(C.byref(panel), S, T, Cf, out.data_ptr(),
-                                             _cabi.F32 if dtype == torch.float32 else _cabi.BF16, _stream())
+        with _on(self.device):
+            rc = _cabi.lib().fvae_gather_windows(C.byref(panel), S, T, Cf, out.data_ptr(),
+                                                 _cabi.F32 if dtype == torch.float32 else _cabi.BF16, _stream(self.device))
         _cabi.check(rc, "fvae_gather_windows")
         return out

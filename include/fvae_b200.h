@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FVAE_ABI_VERSION 2
+#define FVAE_ABI_VERSION 3
 
 /* status codes (<0: argument errors) */
 #define FVAE_OK 0
@@ -160,6 +160,13 @@ int fvae_fe_backward(const fvae_shape* shape, const fvae_panel* x, const float* 
  * events for the per-kernel roofline. */
 int fvae_debug_front_forward(const fvae_shape* shape, const fvae_panel* x, void* workspace, int64_t workspace_bytes,
                              void* stream);
+
+/* diagnostics: the noise a FVAE_FLAG_PHILOX step with this key draws -- eps[S] (module.py:104) and keep_mask[S][K]
+ * (1 = keep; dropout on the attention scores, module.py:132,144) for units unit_base .. unit_base+S-1, evaluated by the
+ * same device functions the step's kernels call.  Parity tests replay a Philox step through the CPU oracle with it and
+ * measure the keep rate; either output may be NULL. */
+int fvae_debug_noise(uint64_t seed, uint64_t step, int64_t unit_base, int64_t S, int32_t K, float* eps,
+                     uint8_t* keep_mask, void* stream);
 
 /* device e[S][H] of the last forward on this workspace (for tests / diagnostics). */
 const float* fvae_workspace_latent(const fvae_shape* shape, int32_t precision, const void* workspace);

@@ -186,7 +186,7 @@ def test_module_dropin_forward_backward(cuda_device):
     with torch.no_grad():
         yp = m.prediction(x)
     assert yp.shape == (x.shape[0], 1) and torch.isfinite(yp).all()
-    fb.set_default_precision("auto")
+    fb.set_default_precision("fp32")
 
 
 def test_philox_noise_is_shard_invariant_and_sane(cuda_device):

@@ -1,0 +1,74 @@
+"""Date sharding does not change the step: the gradient all-reduced over G shards of a
+global batch equals the G = 1 gradient of the same batch to fp32 round-off, the loss is identical, per-unit outputs are
+bit-identical (the noise is keyed by the GLOBAL unit id).  One GPU: the all-reduce is emulated by summing the shards' buffers;
+two or more GPUs: the real NCCL path under torch.distributed.run (tests/_shard_worker.py)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("G", [2, 4])
+def test_sharded_gradient_equals_single_gpu_gradient_emulated(precision, G, cuda_device):
+    from factorvae_b200 import engine
+    from factorvae_b200.batched import DateShardedStep, shard_dates
+    import factorvae_b200 as fb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _shard_worker import make_batch
+    dev = cuda_device
+    H = K = 20
+    T = 6
+    counts = [300, 257, 128, 301, 64, 299, 300, 190]
+    B = len(counts)
+    torch.manual_seed(42)
+    m = fb.FactorVAE(fb.FeatureExtractor(158, H), fb.FactorEncoder(K, 128, H), fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, K)),
+                     fb.FactorPredictor(H, K))
+    L = engine.ParamLayout(158, H, K, 128)
+    flat = L.pack(m.state_dict(), dev)
+    xs, ys = make_batch(dev, counts, T)
+    cs = torch.tensor([0] + counts).cumsum(0)
+    solo = DateShardedStep(L, flat, precision=precision, seed=11)
+    o1, _ = solo.step(torch.cat(xs), torch.cat(ys), cs.to(torch.int32).to(dev), global_dates=B, unit_base=0, train=True)
+    g1, l1 = solo.grad.double().clone(), float(solo.loss.item())
+    total = torch.zeros(L.total + 4, dtype=torch.float64, device=dev)
+    for r in range(G):
+        d0, d1 = shard_dates(B, G, r)
+        ptr = (cs[d0:d1 + 1] - cs[d0]).to(torch.int32).to(dev)
+        part = DateShardedStep(L, flat, precision=precision, seed=11)          # world = 1: scales by B_local / B_global
+        o, _ = part.step(torch.cat(xs[d0:d1]), torch.cat(ys[d0:d1]), ptr, global_dates=B, unit_base=int(cs[d0]), train=True)
+        total += part.gradbuf.double()                                         # what all-reduce(SUM) would produce
+        a, b = int(cs[d0]), int(cs[d1])
+        assert torch.equal(o["yhat"], o1["yhat"][a:b]) and torch.equal(o["mu_y"], o1["mu_y"][a:b])
+        assert torch.equal(o["mu_prior"], o1["mu_prior"][d0:d1])
+    gG, lG = total[: L.total], float(total[L.total])
+    assert abs(lG - l1) <= 1e-6 * abs(l1), (lG, l1)
+    assert float((gG - g1).norm() / g1.norm()) <= 2e-6
+    assert float((gG - g1).abs().max() / g1.abs().max()) <= 2e-5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_sharded_gradient_equals_single_gpu_gradient_nccl(precision):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2|4|8; the 1-GPU emulation above always runs)")
+    G = 8 if n >= 8 else (4 if n >= 4 else 2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={G}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_shard_worker.py"), precision]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    sys.stdout.write(r.stdout[-4000:])
+    assert r.returncode == 0, (r.stdout[-4000:], r.stderr[-4000:])
