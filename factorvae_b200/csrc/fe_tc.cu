@@ -25,6 +25,8 @@
 //                            dxn = dpre . W1 contraction of the reference's autograd is never computed)
 //
 // All operand tiles use the chunk-major SWIZZLE_NONE layout of tc_sm100.cuh.
+#include <cstdlib>
+
 #include "fe.cuh"
 #include "tc_sm100.cuh"
 
@@ -79,7 +81,9 @@ __host__ __device__ inline bool unperm_col(int col, int H, int& gate, int& j) {
 // ---- workspace -----------------------------------------------------------------------------------
 struct TcWs {
     __nv_bfloat16 *w1g, *wih, *wihT, *whh, *whhT;   // operand images
+    __nv_bfloat16 *w1n;                             // W1 diag(gamma) image WITHOUT the bias column (TMA kernels: bias added in the epilogue)
     float *b1f, *bgi, *bhn;                         // [CP], [NC], [HP]
+    float *w1s;                                     // [CP] row sums of the bf16-rounded W1 diag(gamma) image (LayerNorm-after-GEMM fold)
     __nv_bfloat16 *gi;      // [NT][T][NC/8][128][8]   gate pre-activations, then (backward) their gradients
     __nv_bfloat16 *hall;    // [NT][T][HP/8][128][8]   h_t operand tiles (column H = 1)
     __nv_bfloat16 *xh;      // [NT][T][CP/8][128][8]   xhat = LayerNorm(x) operand tiles (column C = 1), saved for backward
@@ -101,6 +105,8 @@ TcWs carve_tc(const FeDims& d, void* base) {
     w.wihT = reinterpret_cast<__nv_bfloat16*>(take(int64_t(NC / 8) * CP * 16));
     w.whh = reinterpret_cast<__nv_bfloat16*>(take(int64_t(HP / 8) * NC * 16));
     w.whhT = reinterpret_cast<__nv_bfloat16*>(take(int64_t(NC / 8) * HP * 16));
+    w.w1n = reinterpret_cast<__nv_bfloat16*>(take(W1_BYTES));
+    w.w1s = reinterpret_cast<float*>(take(CP * 4));
     w.b1f = reinterpret_cast<float*>(take(CP * 4));
     w.bgi = reinterpret_cast<float*>(take(NC * 4));
     w.bhn = reinterpret_cast<float*>(take(HP * 4));
@@ -133,8 +139,10 @@ __global__ void tc_prep_kernel(PrepArgs a) {
     // W1g[n][k] = W1[n][k] * gamma[k]
     for (int idx = tid; idx < CP * CP; idx += nth) {
         const int n = idx / CP, k = idx % CP;
+        const float wv = (n < C && k < C) ? a.W1[n * C + k] * a.ln_w[k] : 0.f;
+        put_img(a.ws.w1n, CP, n, k, wv);         // no bias column: the TMA kernels add b1f in the epilogue
         if (k == C) continue;                    // column C carries the folded bias (written below by another thread)
-        put_img(a.ws.w1g, CP, n, k, (n < C && k < C) ? a.W1[n * C + k] * a.ln_w[k] : 0.f);
+        put_img(a.ws.w1g, CP, n, k, wv);
     }
     // W_ih (rows permuted) and its transpose
     for (int idx = tid; idx < NC * CP; idx += nth) {
@@ -167,6 +175,13 @@ __global__ void tc_prep_kernel(PrepArgs a) {
             a.ws.b1f[n] = v;
             put_img(a.ws.w1g, CP, n, C, v);
         }
+        // w1s[n] = sum_k bf16(W1[n][k] gamma[k]): the sum of the ROUNDED operands the tensor core multiplies
+        float ws_ = 0.f;
+        if (n < C)
+            for (int k = part; k < C; k += 8) ws_ += __bfloat162float(__float2bfloat16(a.W1[n * C + k] * a.ln_w[k]));
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) ws_ += __shfl_xor_sync(0xffffffffu, ws_, s);
+        if (part == 0) a.ws.w1s[n] = ws_;
     }
     for (int col = tid; col < NC; col += nth) {
         int gate, j;
@@ -179,6 +194,7 @@ __global__ void tc_prep_kernel(PrepArgs a) {
 }
 
 #include "fe_tc_front.cuh"   // ItemArgs, staging + LayerNorm, K1 front forward, K4 front backward
+#include "fe_tc_tma.cuh"     // warp-specialised TMA-fed front kernels (dense bf16 panels)
 
 // ---- K2: GRU forward -------------------------------------------------------------------------------------------
 struct GruArgs {
@@ -708,6 +724,28 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
     const int nsm = num_sms();
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
+    if (tma_panel_ok(x, d) && !getenv("FVAE_FRONT_CPASYNC")) {
+        CUtensorMap m128, m64;
+        if (make_panel_map(&m128, x, d, 64, CU_TENSOR_MAP_SWIZZLE_128B) && make_panel_map(&m64, x, d, 32, CU_TENSOR_MAP_SWIZZLE_64B)) {
+            TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, ws};
+            const size_t fixed = A_BYTES + W1_BYTES + size_t(KCH) * NC * 16 + 2 * CP * 4 + 4 * TM * 8 + 256 + 1024;
+            const int xst = (fixed + 2 * XSTAGE <= kMaxSmem) ? 2 : 1;
+            const int ngi = (320 + 2 * NC <= 512) ? 2 : 1;
+            const size_t smem_t = fixed + size_t(xst) * XSTAGE;
+            if (smem_t <= kMaxSmem && 320 + NC <= 512) {
+                auto go = [&](auto kern) -> int {
+                    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_t));
+                    if (ce != cudaSuccess) return int(ce);
+                    kern<<<grid, TF_THREADS, smem_t, st>>>(m128, m64, ta); count_launch();
+                    return int(cudaGetLastError());
+                };
+                if (xst == 2 && ngi == 2) return go(tc_front_tma_kernel<2, 2, true>);
+                if (xst == 2) return go(tc_front_tma_kernel<2, 1, true>);
+                if (ngi == 2) return go(tc_front_tma_kernel<1, 2, true>);
+                return go(tc_front_tma_kernel<1, 1, true>);
+            }
+        }
+    }
     const size_t tail = (CP + NC + 2 * NSPLIT * TM) * 4 + TM + 64;
     const size_t with_stage = W1_BYTES + size_t(KCH) * NC * 16 + 2 * A_BYTES + STAGE_BYTES + tail;
     a.prefetch = (x.dtype == FVAE_BF16 && with_stage <= kMaxSmem) ? 1 : 0;

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace fvae {
 namespace tc {
@@ -46,6 +47,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) asm volatile("trap;");
+    }
+}
+
+// same, naming the wait site before the trap (the warp-specialised kernels have a dozen hand-offs: a phase bug must say where)
+__device__ __forceinline__ void mbar_wait_site(uint64_t* bar, uint32_t parity, int site) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("fvae: mbarrier wait timed out: site %d block %d thread %d parity %u\n", site, int(blockIdx.x), int(threadIdx.x), parity);
+            asm volatile("trap;");
+        }
     }
 }
 

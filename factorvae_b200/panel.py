@@ -119,6 +119,7 @@ class ResidentPanel:
         self.idx_mat = torch.from_numpy(index.idx_mat).to(dev)
         self.sample_date = torch.from_numpy(index.sample_date).to(dev)
         self.sample_inst = torch.from_numpy(index.sample_inst).to(dev)
+        self._batch_cache = {}
 
     @staticmethod
     def from_dataframe(df, num_features: int, device, start=None, end=None, dtype=torch.bfloat16) -> "ResidentPanel":
@@ -144,17 +145,26 @@ class ResidentPanel:
     def batch(self, dates: Sequence[int], T: int, fill: str = "ffill+bfill") -> Tuple[IndexedWindows, torch.Tensor, torch.Tensor]:
         """Windows (as an index), labels y (S,) and the CSR date_ptr (B+1,) of the given batches (positions in date order,
         any order / subset: a shuffled epoch is a permutation of range(num_batches))."""
-        dp = self.index.date_ptr
-        dates = [int(d) for d in dates]
-        counts = np.array([dp[d + 1] - dp[d] for d in dates], dtype=np.int64)
-        contiguous = all(dates[k + 1] == dates[k] + 1 for k in range(len(dates) - 1))
-        if contiguous:
-            sd = self.sample_date[dp[dates[0]]:dp[dates[-1] + 1]]
-            sj = self.sample_inst[dp[dates[0]]:dp[dates[-1] + 1]]
-        else:
-            sel = torch.from_numpy(np.concatenate([np.arange(dp[d], dp[d + 1]) for d in dates])).to(self.device)
-            sd, sj = self.sample_date[sel].contiguous(), self.sample_inst[sel].contiguous()
-        S = int(counts.sum())
+        # the host side of a batch (sample slices, counts, the CSR date_ptr on the device) depends only on WHICH dates are asked
+        # for: cached, so a training loop that revisits a batch pays one kernel launch, no host numpy work and no pageable H2D
+        key = (dates.start, dates.stop, dates.step) if isinstance(dates, range) else tuple(int(d) for d in dates)
+        hit = self._batch_cache.get(key)
+        if hit is None:
+            dp = self.index.date_ptr
+            dl = [int(d) for d in dates]
+            counts = np.array([dp[d + 1] - dp[d] for d in dl], dtype=np.int64)
+            contiguous = all(dl[k + 1] == dl[k] + 1 for k in range(len(dl) - 1))
+            if contiguous:
+                sd = self.sample_date[dp[dl[0]]:dp[dl[-1] + 1]]
+                sj = self.sample_inst[dp[dl[0]]:dp[dl[-1] + 1]]
+            else:
+                sel = torch.from_numpy(np.concatenate([np.arange(dp[d], dp[d + 1]) for d in dl])).to(self.device)
+                sd, sj = self.sample_date[sel].contiguous(), self.sample_inst[sel].contiguous()
+            date_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(self.device)
+            if len(self._batch_cache) > 4096:
+                self._batch_cache.clear()
+            hit = self._batch_cache[key] = (sd, sj, int(counts.sum()), date_ptr)
+        sd, sj, S, date_ptr = hit
         row_index = torch.empty(S, T, dtype=torch.int32, device=self.device)
         y = torch.empty(S, dtype=torch.float32, device=self.device)
         D, I = self.index.idx_mat.shape
@@ -163,7 +173,6 @@ class ResidentPanel:
                                                self.index.nan_row, row_index.data_ptr(), self.label.data_ptr(), y.data_ptr(),
                                                _stream(self.device))
         _cabi.check(rc, "fvae_window_index")
-        date_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(self.device)
         return IndexedWindows(self.table, row_index, self.C), y, date_ptr
 
     def windows(self, xw: IndexedWindows, dtype=torch.float32) -> torch.Tensor:

@@ -100,7 +100,8 @@ def main():
         score_shape = list(frame.shape)
         scores_finite = bool(np.isfinite(frame["score"].to_numpy()).all())
     except Exception as e:                            # reported, not hidden
-        score_shape, scores_finite = f"{type(e).__name__}: {e}", False
+        import traceback
+        score_shape, scores_finite = f"{type(e).__name__}: {e} | " + traceback.format_exc()[-600:], False
     print(json.dumps({"module_file": used_module.__file__, "device": str(next(model.parameters()).device), "epochs": epochs,
                       "checkpoint": ckpt, "state_keys": len(state), "load_state_dict": str(missing), "reloaded_val_loss": v1,
                       "score_frame_shape": score_shape, "scores_finite": scores_finite}))

@@ -22,7 +22,9 @@ def _drive(module_dir, work, env_extra=None):
     env = dict(os.environ, WANDB_MODE="disabled", **(env_extra or {}))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_dropin_driver.py"), module_dir, REF, str(work)],
                        capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
-    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    if r.returncode != 0:
+        sys.stdout.write("---- driver stdout ----\n" + r.stdout[-3000:] + "\n---- driver stderr ----\n" + r.stderr[-6000:])
+    assert r.returncode == 0, r.stderr[-1500:]
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
@@ -31,6 +33,7 @@ def test_unmodified_reference_drivers_train_on_the_dropin(precision, tmp_path, c
     if not os.path.exists(os.path.join(REF, "main.py")):
         pytest.skip("baseline/_ref is absent (built by __graft_entry__.build() where /root/reference is mounted)")
     ours = _drive(os.path.join(ROOT, "dropin"), tmp_path / "ours", {"FVAE_PRECISION": precision})
+    print("drop-in driver result:", ours)
     assert ours["module_file"].startswith(os.path.join(ROOT, "dropin")), ours["module_file"]
     assert ours["device"].startswith("cuda")
     ep = ours["epochs"]

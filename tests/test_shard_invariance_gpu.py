@@ -46,7 +46,12 @@ def test_sharded_gradient_equals_single_gpu_gradient_emulated(precision, G, cuda
         total += part.gradbuf.double()                                         # what all-reduce(SUM) would produce
         a, b = int(cs[d0]), int(cs[d1])
         assert torch.equal(o["yhat"], o1["yhat"][a:b]) and torch.equal(o["mu_y"], o1["mu_y"][a:b])
-        assert torch.equal(o["mu_prior"], o1["mu_prior"][d0:d1])
+        # per-date vectors: bit-identical in fp32 mode; the tensor-core heads distribute whole dates over persistent CTAs, the
+        # order of their fp32 partial sums follows the CTA a date lands on -> last-bit differences
+        if precision == "fp32":
+            assert torch.equal(o["mu_prior"], o1["mu_prior"][d0:d1])
+        else:
+            assert torch.allclose(o["mu_prior"], o1["mu_prior"][d0:d1], rtol=1e-5, atol=1e-6)
     gG, lG = total[: L.total], float(total[L.total])
     assert abs(lG - l1) <= 1e-6 * abs(l1), (lG, l1)
     assert float((gG - g1).norm() / g1.norm()) <= 2e-6
