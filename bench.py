@@ -315,7 +315,9 @@ def main():
 
     # synthetic panel: N(0,1) clipped to +-3 per GLOBAL date id (identical global batch for any sharding)
     pdt = torch.bfloat16 if args.panel == "bf16" else torch.float32
-    x = torch.empty(S, T, C_FEATURES, dtype=pdt, device=dev)
+    # rows padded to a 16-byte pitch ([S][T][160], 158 features used): every row is then a legal TMA box row (+1.3 % bytes)
+    x_store = torch.zeros(S, T, 160 if pdt == torch.bfloat16 else C_FEATURES, dtype=pdt, device=dev)
+    x = x_store[:, :, :C_FEATURES]
     y = torch.empty(S, dtype=torch.float32, device=dev)
     gen = torch.Generator(device=dev)
     for d in range(B):
@@ -561,7 +563,8 @@ def main():
                 "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": args.workload_desc},
                 "detail": {"panel_dtype": args.panel, "precision": precision,
-                           "l2": "inputs larger than L2 (panel %.0f MB per GPU)" % (x.numel() * x.element_size() / 1e6),
+                           "l2": "inputs larger than L2 (panel %.0f MB per GPU)" % (x_store.numel() * x_store.element_size() / 1e6),
+                           "panel_layout": "x[S][T][%d] %s, %d features per row used (row pitch padded to 16 bytes)" % (x_store.shape[2], args.panel, C_FEATURES),
                            "noise": "in-kernel Philox (eps + dropout masks), keyed by global unit id",
                            "parallelism": f"dp{world} over dates", "dates_per_gpu": B, "micro_batch_dates": micro,
                            "collective": "one all-reduce of the flat fp32 gradient (+ loss) per step" if world > 1 else "none"},

@@ -9,11 +9,13 @@
 //      at all, where the xhat tile was a second rounding); mean / rstd are two per-row scalars applied in the epilogue that
 //      reads the accumulator anyway.  No normalised tile is built, stored or re-read.  Backward uses the same identity:
 //          Q = dpre^T [xhat | 1]  =  (dpre rstd)^T [x | 1/rstd | mean]   ->  Q[o][i] = D[o][i] - D[o][C+1],  db1[o] = D[o][C]
-//  (2) C = 158 bf16 rows are 316 bytes: no 16-byte row pitch, so the panel is described to TMA as the 2-D tensor
-//      [S][T*C] (row pitch T*C*2 = 6320 B, a multiple of 16) and the 128 rows of item (tile, t) are the box at element
-//      coordinate (t*C, tile*128): TMA takes arbitrary element coordinates, the box lands in the 128-byte-swizzled K-major
-//      operand layout the UMMA reads, columns C.. of the box are the first features of the next time step (zero-filled
-//      past the end of the sequence) and meet zero rows of the weight image.
+//  (2) TMA needs every box row to start on a 16-byte boundary (measured: an innermost coordinate that is not a multiple of
+//      8 bf16 elements faults, scripts/probe/tma_probe.cu), and C = 158 bf16 rows are 316 bytes.  So the TMA kernels take
+//      panels whose ROW PITCH is a multiple of 8 elements (x[S][T][160] with 158 features used: +1.3 % bytes; the resident
+//      row table has had that pitch since round 1).  The panel is the 3-D tensor [S][T][C] with strides (seq_pitch,
+//      row_pitch); the 128 rows of item (tile, t) are the box {64, 1, 128} at (0 | 64 | 128, t, tile*128) and land directly in
+//      the 128-byte-swizzled K-major operand layout the UMMA reads.  The tensor's innermost extent is C, so columns C..159 of
+//      the box are out of bounds and arrive as zeros whatever the padding holds.  Dense pitch-158 panels keep the cp.async path.
 //
 // Roles (576 threads, one CTA per SM, persistent over items; every hand-off is an mbarrier, no CTA barrier in steady state):
 //   warp 0      producer   : three tensor-map loads per item (2 x [128 x 64] SWIZZLE_128B + [128 x 32] SWIZZLE_64B = 40 KB)
@@ -41,9 +43,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t l
     d |= uint64_t(layout_type & 7u) << 61;          // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
     return d;
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -155,9 +157,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
                 const int t = int(item - st * a.T);
                 unsigned char* dst = sX + s * XSTAGE;
                 mbar_expect_tx(&x_full[s], XSTAGE);
-                tma_load_2d(dst + XB0, &map128, t * C, int(st * TM), &x_full[s]);
-                tma_load_2d(dst + XB1, &map128, t * C + 64, int(st * TM), &x_full[s]);
-                tma_load_2d(dst + XB2, &map64, t * C + 128, int(st * TM), &x_full[s]);
+                tma_load_3d(dst + XB0, &map128, 0, t, int(st * TM), &x_full[s]);
+                tma_load_3d(dst + XB1, &map128, 64, t, int(st * TM), &x_full[s]);
+                tma_load_3d(dst + XB2, &map64, 128, t, int(st * TM), &x_full[s]);
             }
         }
     } else if (warp == 1) {
@@ -327,20 +329,20 @@ inline PFN_encodeTiled get_encode_tiled() {
     }
     return fn;
 }
-// the dense bf16 panel as [S][T*C]; box = [128 rows][box_cols]
+// the dense bf16 panel as the 3-D tensor [S][T][C] (strides seq_pitch, row_pitch); box = [128 sequences][1 time step][box_cols]
 inline bool make_panel_map(CUtensorMap* m, const fvae_panel& x, const FeDims& d, uint32_t box_cols, CUtensorMapSwizzle sw) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
-    const cuuint64_t dims[2] = {cuuint64_t(d.T) * cuuint64_t(d.C), cuuint64_t(d.S)};
-    const cuuint64_t strides[1] = {cuuint64_t(x.seq_pitch) * 2};
-    const cuuint32_t box[2] = {box_cols, TM};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x.data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t dims[3] = {cuuint64_t(d.C), cuuint64_t(d.T), cuuint64_t(d.S)};
+    const cuuint64_t strides[2] = {cuuint64_t(x.row_pitch) * 2, cuuint64_t(x.seq_pitch) * 2};
+    const cuuint32_t box[3] = {box_cols, 1, TM};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x.data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// can this panel take the TMA kernels?
+// can this panel take the TMA kernels?  bf16, dense windows, every row 16-byte aligned (pitches multiples of 8 elements)
 inline bool tma_panel_ok(const fvae_panel& x, const FeDims& d) {
-    return x.dtype == FVAE_BF16 && x.row_index == nullptr && x.row_pitch == d.C && d.C == 158 &&
-           (reinterpret_cast<uintptr_t>(x.data) & 15u) == 0 && ((x.seq_pitch * 2) & 15) == 0 && x.seq_pitch >= int64_t(d.T) * d.C &&
-           int64_t(d.T) * d.C < (int64_t(1) << 31) && get_encode_tiled() != nullptr;
+    return x.dtype == FVAE_BF16 && x.row_index == nullptr && d.C > 128 && d.C < CP && (x.row_pitch & 7) == 0 && (x.seq_pitch & 7) == 0 &&
+           (reinterpret_cast<uintptr_t>(x.data) & 15u) == 0 && x.row_pitch >= d.C && x.seq_pitch >= int64_t(d.T - 1) * x.row_pitch + d.C &&
+           get_encode_tiled() != nullptr;
 }

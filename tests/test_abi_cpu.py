@@ -145,3 +145,16 @@ def test_next_row_modules_have_no_cpu_fallback(cabi):
     idx = PanelIndex(np.zeros((2, 2), np.int32), np.zeros(1, np.int32), np.zeros(1, np.int32), np.array([0, 1]), 4)
     with pytest.raises(RuntimeError):
         ResidentPanel(np.zeros((4, 3), np.float32), idx, 2, "cpu")
+
+
+def test_dropin_module_reexports_what_the_reference_module_leaks():
+    """utils.py:6 does `from module import *` and uses pd / np / torch that the reference's module.py imports at its top
+    (module.py:2-8, no __all__): the drop-in must leak the same names."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); ns = {}; exec('from module import *', ns); "
+            "missing = [n for n in ('torch','nn','F','optim','DataLoader','Dataset','TensorDataset','pd','np','FactorVAE',"
+            "'FeatureExtractor','FactorEncoder','FactorDecoder','FactorPredictor','AlphaLayer','BetaLayer','AttentionLayer') if n not in ns]; "
+            "print(missing); sys.exit(1 if missing else 0)") % os.path.join(ROOT, "dropin")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout, r.stderr[-800:])

@@ -33,8 +33,10 @@ def _build(H, K, M=128, seed=42):
 
 
 def _panel(B, N, T, dev, dtype=torch.bfloat16):
-    """bench.py's synthetic panel: per global date id, N(0,1) clipped to +-3, rounded to the panel dtype."""
-    x = torch.empty(B * N, T, C, dtype=dtype, device=dev)
+    """bench.py's synthetic panel: per global date id, N(0,1) clipped to +-3, rounded to the panel dtype; rows padded to a
+    16-byte pitch (160 elements, 158 used) exactly as bench.py lays it out -- the layout the TMA kernels take."""
+    store = torch.full((B * N, T, 160), 7.0, dtype=dtype, device=dev)           # padding holds junk: it must never be read
+    x = store[:, :, :C]
     y = torch.empty(B * N, dtype=torch.float32, device=dev)
     gen = torch.Generator(device=dev)
     for d in range(B):

@@ -256,7 +256,9 @@ def test_bf16_tc_latent_close_to_fp32_kernels_multi_tile(cuda_device):
     flat = L.pack(m.state_dict(), cuda_device)
     x = torch.randn(333, 7, 158, device=cuda_device).clamp_(-3, 3)
     e32, _ = engine.fe_forward(L, flat, x, "fp32")
-    for xin in (x, x.to(torch.bfloat16), torch.cat([x, x[:, :, :1]], dim=2)[:, :, :158]):
+    padded = torch.full((333, 7, 160), 5.0, device=cuda_device, dtype=torch.bfloat16)      # 16-byte row pitch: the TMA kernels
+    padded[:, :, :158] = x.to(torch.bfloat16)
+    for xin in (x, x.to(torch.bfloat16), torch.cat([x, x[:, :, :1]], dim=2)[:, :, :158], padded[:, :, :158]):
         e16, _ = engine.fe_forward(L, flat, xin, "bf16")
         ref = engine.fe_forward(L, flat, xin.float(), "fp32")[0] if xin.dtype == torch.bfloat16 else e32
         assert float((e16 - ref).abs().max()) <= 2e-2, float((e16 - ref).abs().max())
@@ -302,6 +304,19 @@ def test_bf16_tc_chain_vs_fp32_kernels(shape, cuda_device):
     assert not bad, (bad, report)
     assert _cos(g16, g32) >= 0.999
     assert float((g16.double() - g32.double()).norm() / g32.double().norm()) <= 3e-2
+    # the same step from a bf16 panel with a 16-byte row pitch (the layout the TMA-fed kernels take) against the fp32
+    # kernels on the same bf16 values
+    store = torch.full((S, T, 160), -3.0, device=cuda_device, dtype=torch.bfloat16)
+    store[:, :, :158] = x.to(torch.bfloat16)
+    xb = store[:, :, :158]
+    ob, stb = engine.elbo_forward(L, flat, xb, y, ptr, train=True, precision="bf16", philox=(9, 1, 0))
+    gb, eb = engine.elbo_backward(L, stb).clone(), engine.latent(stb)
+    of, stf = engine.elbo_forward(L, flat, xb.float(), y, ptr, train=True, precision="fp32", philox=(9, 1, 0))
+    gf, ef = engine.elbo_backward(L, stf).clone(), engine.latent(stf)
+    assert float((eb - ef).abs().max()) <= 2e-2
+    assert abs(float(ob["loss"]) - float(of["loss"])) <= 2e-2 * abs(float(of["loss"]))
+    assert _cos(gb, gf) >= 0.999
+    assert float((gb.double() - gf.double()).norm() / gf.double().norm()) <= 3e-2
 
 
 @pytest.mark.parametrize("case", ["ragged", "many_dates", "one_date_many_tiles", "guard", "max_shape", "tiny_shape"])
