@@ -89,6 +89,7 @@ struct TcWs {
     __nv_bfloat16 *xh;      // [NT][T][CP/8][128][8]   xhat = LayerNorm(x) operand tiles (column C = 1), saved for backward
     __nv_bfloat16 *u;       // [NT][T][CP/8][128][8]   u = LeakyReLU(pre) operand tiles (column C = 1), saved for backward
     unsigned long long *mask;  // [NT][T][4][128]      LeakyReLU' sign bits of my 40 columns (bit b: pre > 0)
+    float2 *stats;             // [NT][T][128]         row statistics (-mean rstd, rstd) saved by the TMA front kernel
     float *q;               // [2*128][CP]  Q = dpre^T [xhat|1]
     float *dwih;            // [2*128][CP]  dGI^T [u|1]   (permuted rows)
     int64_t bytes;
@@ -116,6 +117,7 @@ TcWs carve_tc(const FeDims& d, void* base) {
     // u tiles are saved only when backward cannot rebuild them (tc_wih_recompute_kernel covers NC <= 128)
     w.u = NC <= 128 ? nullptr : reinterpret_cast<__nv_bfloat16*>(take(NT * d.T * int64_t(A_BYTES)));
     w.mask = reinterpret_cast<unsigned long long*>(take(NT * d.T * int64_t(4 * TM * 8)));
+    w.stats = reinterpret_cast<float2*>(take(NT * d.T * int64_t(TM * 8)));
     w.q = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
     w.dwih = reinterpret_cast<float*>(take(int64_t(256) * CP * 4));
     w.bytes = p - static_cast<char*>(base);
@@ -609,10 +611,11 @@ struct PostArgs {
 __global__ void tc_post_kernel(PostArgs a) {
     const int C = a.C, H = a.H;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    // dW1[o][i] = Q[o][i] gamma[i] + db1[o] beta[i];  db1[o] = Q[o][C]
+    // dW1[o][i] = Q[o][i] gamma[i] + db1[o] beta[i];  db1[o] = Q[o][C].  Column C+1 is the LayerNorm-fold correction of the
+    // TMA kernels, Q[o][i] = D[o][i] - D[o][C+1] (fe_tc_tma.cuh); the streaming kernels leave it at zero (xhat[:, C+1] = 0).
     for (int idx = tid; idx < C * C; idx += nth) {
         const int o = idx / C, i = idx % C;
-        atomicAdd(a.g.W1 + idx, a.q[o * CP + i] * a.ln_w[i] + a.q[o * CP + C] * a.ln_b[i]);
+        atomicAdd(a.g.W1 + idx, (a.q[o * CP + i] - a.q[o * CP + C + 1]) * a.ln_w[i] + a.q[o * CP + C] * a.ln_b[i]);
     }
     for (int o = tid; o < C; o += nth) atomicAdd(a.g.b1 + o, a.q[o * CP + C]);
     // dgamma[i] = sum_o W1[o][i] Q[o][i];  dbeta[i] = sum_o W1[o][i] db1[o]
@@ -623,7 +626,7 @@ __global__ void tc_post_kernel(PostArgs a) {
         if (i < C)
             for (int o = part; o < C; o += 8) {
                 const float w = a.W1[o * C + i];
-                dg = fmaf(w, a.q[o * CP + i], dg);
+                dg = fmaf(w, a.q[o * CP + i] - a.q[o * CP + C + 1], dg);
                 db = fmaf(w, a.q[o * CP + C], db);
             }
 #pragma unroll
@@ -724,10 +727,10 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
     const int nsm = num_sms();
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
-    if (tma_panel_ok(x, d) && !getenv("FVAE_FRONT_CPASYNC")) {
+    if (tma_panel_ok(x, d)) {
         CUtensorMap m128, m64;
-        if (make_panel_map(&m128, x, d, 64, CU_TENSOR_MAP_SWIZZLE_128B) && make_panel_map(&m64, x, d, 32, CU_TENSOR_MAP_SWIZZLE_64B)) {
-            TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, ws};
+        if (make_x_maps(&m128, &m64, x, d)) {
+            TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), ws};
             const size_t fixed = A_BYTES + W1_BYTES + size_t(KCH) * NC * 16 + 2 * CP * 4 + 4 * TM * 8 + 256 + 1024;
             const int xst = (fixed + 2 * XSTAGE <= kMaxSmem) ? 2 : 1;
             const int ngi = (320 + 2 * NC <= 512) ? 2 : 1;
@@ -739,10 +742,14 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
                     kern<<<grid, TF_THREADS, smem_t, st>>>(m128, m64, ta); count_launch();
                     return int(cudaGetLastError());
                 };
-                if (xst == 2 && ngi == 2) return go(tc_front_tma_kernel<2, 2, true>);
-                if (xst == 2) return go(tc_front_tma_kernel<2, 1, true>);
-                if (ngi == 2) return go(tc_front_tma_kernel<1, 2, true>);
-                return go(tc_front_tma_kernel<1, 1, true>);
+                const bool idx = x.row_index != nullptr, xh = !tma_fused_backward_ok(x, d);
+#define FVAE_TF(XS, NG) (idx ? (xh ? go(tc_front_tma_kernel<XS, NG, true, true>) : go(tc_front_tma_kernel<XS, NG, false, true>)) \
+                             : (xh ? go(tc_front_tma_kernel<XS, NG, true, false>) : go(tc_front_tma_kernel<XS, NG, false, false>)))
+                if (xst == 2 && ngi == 2) return FVAE_TF(2, 2);
+                if (xst == 2) return FVAE_TF(2, 1);
+                if (ngi == 2) return FVAE_TF(1, 2);
+                return FVAE_TF(1, 1);
+#undef FVAE_TF
             }
         }
     }
@@ -804,6 +811,24 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     if (ce != cudaSuccess) return int(ce);
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
+    if (tma_fused_backward_ok(x, d)) {
+        // one fused kernel: raw x rows (TMA) + dGI tiles (bulk copies) read once; GEMM1 recomputed; Q and dW_ih accumulated in TMEM
+        CUtensorMap m128, m64;
+        if (!make_x_maps(&m128, &m64, x, d)) return FVAE_ERR_UNSUPPORTED;
+        TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), ws};
+        cudaError_t ce2;
+        if (x.row_index) {
+            if ((ce2 = cudaFuncSetAttribute(tc_back_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TB_SMEM))) != cudaSuccess) return int(ce2);
+            tc_back_tma_kernel<true><<<grid, TB_THREADS, TB_SMEM, st>>>(m128, m64, ta); count_launch();
+        } else {
+            if ((ce2 = cudaFuncSetAttribute(tc_back_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TB_SMEM))) != cudaSuccess) return int(ce2);
+            tc_back_tma_kernel<false><<<grid, TB_THREADS, TB_SMEM, st>>>(m128, m64, ta); count_launch();
+        }
+        if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
+        PostArgs pf{d.C, d.H, NC, w.ln_w, w.ln_b, w.W1, ws.q, ws.dwih, gr};
+        tc_post_kernel<<<64, 256, 0, st>>>(pf); count_launch();
+        return int(cudaGetLastError());
+    }
     {   // Q from the saved xhat tiles / mask bits (the panel is not touched)
         const size_t g_bytes = size_t(NC / 8) * TILE_CH;
         const size_t per_stage = A_BYTES + (g_bytes > A_BYTES ? g_bytes : A_BYTES);          // xhat tile + [dGI -> dpre] tile

@@ -31,11 +31,69 @@ constexpr int TF_W_STAT = 2, TF_W_EPU = 6, TF_W_EPG = 14;      // first warp of 
 constexpr uint32_t XB0 = 0, XB1 = 16384, XB2 = 32768;          // x stage: [128][128B] sw128 | [128][128B] sw128 | [128][64B] sw64
 constexpr uint32_t XSTAGE = 40960;
 
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar);
+
 struct TmaFrontArgs {
     int T, C, NC; int64_t NT;
     int S;
+    const int32_t* row_index;     // resident panel: [S][T] rows of the table (NULL: dense windows)
+    int32_t oob_row;              // a row number past the table: gathered as zeros (sequences beyond S)
     TcWs ws;
 };
+
+// gather4: four table rows (4 x 128 B or 4 x 64 B) land as four consecutive rows of a swizzled block (measured:
+// scripts/probe/gather4_probe.cu; the tensor map's box is {cols, 1})
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* map, int c0, int r0, int r1, int r2, int r3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar)) : "memory");
+}
+
+// The x producer of both TMA kernels (whole warp 0).  Dense windows: lane 0 issues three box loads per item.  Resident
+// panel: lane l gathers rows 4l..4l+3 of the tile (three gather4 per lane; the table rows of the NEXT item are fetched
+// while this item's copies fly).  `release(k)` blocks until stage k % XST may be overwritten.
+template <int XST, bool IDX, typename Release>
+__device__ __forceinline__ void produce_x(const TmaFrontArgs& a, const CUtensorMap* map128, const CUtensorMap* map64, unsigned char* sX,
+                                          uint64_t* x_full, int64_t mine, int64_t G, Release release) {
+    const int lane = threadIdx.x & 31;
+    int4 nxt = make_int4(0, 0, 0, 0);
+    auto fetch_idx = [&](int64_t k) {
+        const int64_t item = int64_t(blockIdx.x) + k * G;
+        const int64_t st = item / a.T;
+        const int t = int(item - st * a.T);
+        int r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t sq = st * TM + 4 * lane + i;
+            r[i] = sq < a.S ? a.row_index[sq * a.T + t] : a.oob_row;
+        }
+        return make_int4(r[0], r[1], r[2], r[3]);
+    };
+    if (IDX && mine > 0) nxt = fetch_idx(0);
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = int(k % XST);
+        if (k >= XST) release(k);
+        unsigned char* dst = sX + s * XSTAGE;
+        if (!IDX) {
+            if (lane == 0) {
+                const int64_t item = int64_t(blockIdx.x) + k * G;
+                const int64_t st = item / a.T;
+                const int t = int(item - st * a.T);
+                mbar_expect_tx(&x_full[s], XSTAGE);
+                tma_load_3d(dst + XB0, map128, 0, t, int(st * TM), &x_full[s]);
+                tma_load_3d(dst + XB1, map128, 64, t, int(st * TM), &x_full[s]);
+                tma_load_3d(dst + XB2, map64, 128, t, int(st * TM), &x_full[s]);
+            }
+        } else {
+            const int4 cur = nxt;
+            if (lane == 0) mbar_expect_tx(&x_full[s], XSTAGE);
+            __syncwarp();
+            tma_gather4(dst + XB0 + lane * 512, map128, 0, cur.x, cur.y, cur.z, cur.w, &x_full[s]);
+            tma_gather4(dst + XB1 + lane * 512, map128, 64, cur.x, cur.y, cur.z, cur.w, &x_full[s]);
+            tma_gather4(dst + XB2 + lane * 256, map64, 128, cur.x, cur.y, cur.z, cur.w, &x_full[s]);
+            if (k + 1 < mine) nxt = fetch_idx(k + 1);
+        }
+    }
+}
 
 // ---- descriptors / loads -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -97,9 +155,10 @@ __device__ __forceinline__ void row_stats(const unsigned char* xs, int row, int 
 
 // ---- K1 (TMA form) --------------------------------------------------------------------------------------------------
 // XST x stages (2 when shared memory allows), NGI GI accumulator sets (2 when 320 + 2 NC <= 512 TMEM columns).
-// SAVE: also write the normalised xhat tile and the LeakyReLU' sign bits the cp.async-era backward kernels stream
-// (transitional / cross-check mode; the fused backward needs neither).
-template <int XST, int NGI, bool SAVE>
+// Always saved for backward: the LeakyReLU' sign bits (40 per thread part) and the row statistics (-mean rstd, rstd).
+// SAVE_XH: also write the normalised xhat tile the cp.async-era backward kernels stream (shapes the fused backward
+// does not cover); IDX: rows come from the resident table through fvae_panel.row_index.
+template <int XST, int NGI, bool SAVE_XH, bool IDX>
 __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __grid_constant__ CUtensorMap map128,
                                                                      const __grid_constant__ CUtensorMap map64, TmaFrontArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -148,20 +207,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
 
     if (warp == 0) {
         // ===== producer =====
-        if (lane == 0) {
-            for (int64_t k = 0; k < mine; ++k) {
-                const int s = int(k % XST);
-                if (k >= XST) mbar_wait_site(&x_empty[s], uint32_t((k / XST) - 1) & 1u, 1);
-                const int64_t item = int64_t(blockIdx.x) + k * G;
-                const int64_t st = item / a.T;
-                const int t = int(item - st * a.T);
-                unsigned char* dst = sX + s * XSTAGE;
-                mbar_expect_tx(&x_full[s], XSTAGE);
-                tma_load_3d(dst + XB0, &map128, 0, t, int(st * TM), &x_full[s]);
-                tma_load_3d(dst + XB1, &map128, 64, t, int(st * TM), &x_full[s]);
-                tma_load_3d(dst + XB2, &map64, 128, t, int(st * TM), &x_full[s]);
-            }
-        }
+        if (IDX || lane == 0)
+            produce_x<XST, IDX>(a, &map128, &map64, sX, x_full, mine, G,
+                                [&](int64_t k) { mbar_wait_site(&x_empty[k % XST], uint32_t((k / XST) - 1) & 1u, 1); });
     } else if (warp == 1) {
         // ===== UMMA issuer =====
         if (lane == 0 && mine > 0) {
@@ -196,8 +244,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
             float mean, rstd;
             row_stats(xs, row, C, mean, rstd);
             sStat[q * TM + row] = make_float2(-mean * rstd, rstd);
-            if (SAVE) {          // the normalised tile (column C = 1) for the streaming backward kernels
-                const int64_t item = int64_t(blockIdx.x) + k * G;
+            const int64_t item = int64_t(blockIdx.x) + k * G;
+            a.ws.stats[size_t(item) * TM + row] = make_float2(-mean * rstd, rstd);     // saved for the fused backward
+            if (SAVE_XH) {       // the normalised tile (column C = 1) for the streaming backward kernels
                 unsigned char* g = reinterpret_cast<unsigned char*>(a.ws.xh) + size_t(item) * A_BYTES;
                 const float shift = -mean * rstd;
 #pragma unroll 4
@@ -245,12 +294,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
                     v[4 * e4 + 2] = fmaf(v[4 * e4 + 2], st2.y, fmaf(st2.x, ww.z, bb.z));
                     v[4 * e4 + 3] = fmaf(v[4 * e4 + 3], st2.y, fmaf(st2.x, ww.w, bb.w));
                 }
-                if (SAVE) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int cc = gq * 16 + e;
-                        if (v[e] > 0.f) { if (cc < 40) mlo |= 1ull << cc; else mhi |= 1ull << (cc - 40); }
-                    }
+                for (int e = 0; e < 16; ++e) {
+                    const int cc = gq * 16 + e;
+                    if (v[e] > 0.f) { if (cc < 40) mlo |= 1ull << cc; else mhi |= 1ull << (cc - 40); }
                 }
                 uint32_t w[8];
 #pragma unroll
@@ -274,8 +321,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
             if (k > 0) mbar_wait_site(u_empty, uint32_t(k - 1) & 1u, 9);   // GEMM2(k-1) has read the u tile
 #pragma unroll
             for (int ch = 0; ch < 10; ++ch) *reinterpret_cast<uint4*>(sU + tile_off(TM, row, 10 * half + ch)) = pk[ch];
-            if (SAVE) {
+            {
                 const int64_t item = int64_t(blockIdx.x) + k * G;
+                if (SAVE_XH && a.ws.u) {          // NC > 128: the streaming dW_ih kernel reads saved u tiles (it cannot rebuild them)
+                    unsigned char* gu = reinterpret_cast<unsigned char*>(a.ws.u) + size_t(item) * A_BYTES;
+#pragma unroll
+                    for (int ch = 0; ch < 10; ++ch) *reinterpret_cast<uint4*>(gu + tile_off(TM, row, 10 * half + ch)) = pk[ch];
+                }
                 unsigned long long* gm = a.ws.mask + size_t(item) * 4 * TM;
                 gm[(2 * half) * TM + row] = mlo;
                 gm[(2 * half + 1) * TM + row] = mhi;
@@ -313,6 +365,294 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// ---- fused front backward (TMA form, NC <= 64) -------------------------------------------------------------------------
+// One kernel instead of K4a (du -> dpre -> Q) + K4b (GEMM1 again -> u -> dW_ih): per item the raw x rows (TMA) and the dGI
+// tile (bulk copy) are read ONCE; nothing but these two, the saved sign bits and the row statistics comes from HBM.
+//   du   = dGI . W_ih                      [128 x 160]  -> dpre' = du * LeakyReLU'(pre) * rstd   (bf16 tile)
+//   pre  = x . W1n^T (GEMM1 recomputed)    [128 x 160]  -> u = LeakyReLU(rstd pre + fold)        (bf16 tile)
+//   Q   += dpre'^T [x | 1/rstd | mean]     (160 x 160: 128 x 160 direct + two transposed 128 x 32 blocks for rows o >= 128)
+//   dWih^T += [u | 1]^T dGI                (160 x 64, transposed: two 128 x 64 blocks)
+// TMEM (512 columns, all used): [0,160) du / pre ALTERNATE | [160,320) QA | [320,352) QB0 | [352,384) QB1 | [384,448) DW0 | [448,512) DW1.
+// Shared memory (224 KB): x 2 x 40 KB | dGI 2 x 16 KB | ONE 40 KB tile that holds dpre'(k) until Q(k) has read it, then u(k)
+// until dW(k) has | W1n image 50 KB | W_ih^T image 20 KB.
+// Per item the tensor pipe runs  du(k) . [E: dpre'] . GEMM1(k), Q(k) . [E: u, under Q] . du(k+1), dW(k) ...  -- 2.6 k cycles of
+// MMA per item against 2 x 0.6 k of epilogue on the critical path.
+// Roles (640 threads): warp 0 producer, warp 1 UMMA issuer, warp 2 writes the two LayerNorm columns (1/rstd, mean) into the
+// landed x stage, warps 4-19 epilogue: thread = (row, 40 columns).
+constexpr int TB_THREADS = 640;
+constexpr int TB_W_EPI = 4;
+constexpr int TB_NC = 64;
+constexpr uint32_t TB_G_BYTES = (TB_NC / 8) * TILE_CH;            // 16384
+constexpr uint32_t TB_OFF_G = 2 * XSTAGE, TB_OFF_UD = TB_OFF_G + 2 * TB_G_BYTES, TB_OFF_W1 = TB_OFF_UD + A_BYTES,
+                   TB_OFF_WT = TB_OFF_W1 + W1_BYTES, TB_OFF_TAIL = TB_OFF_WT + (TB_NC / 8) * CP * 16;
+constexpr size_t TB_SMEM = TB_OFF_TAIL + 2 * CP * 4 + 256 + 1024;
+
+// weight-gradient MMA group over the 128 rows of an item: D[128 x N] (+)= A^T B, A / B given as (descriptor, per-16-row step)
+__device__ __forceinline__ void issue_wgrad_desc(uint32_t tmem_col, uint64_t ad, uint64_t astep, uint64_t bd, uint64_t bstep, uint32_t N, bool acc) {
+    const uint32_t idesc = make_idesc_bf16(kTileRows, N, true, true);
+#pragma unroll
+    for (int ks = 0; ks < int(kTileRows) / 16; ++ks) {
+        mma_bf16_ss(tmem_col, ad, bd, idesc, (acc || ks > 0) ? 1u : 0u);
+        ad += astep; bd += bstep;
+    }
+}
+
+template <bool IDX>
+__global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid_constant__ CUtensorMap map128,
+                                                                    const __grid_constant__ CUtensorMap map64, TmaFrontArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C = a.C;
+    unsigned char* sX = smem;
+    unsigned char* sG = smem + TB_OFF_G;
+    unsigned char* sUD = smem + TB_OFF_UD;
+    unsigned char* sW1 = smem + TB_OFF_W1;
+    unsigned char* sWT = smem + TB_OFF_WT;
+    float* sB1 = reinterpret_cast<float*>(smem + TB_OFF_TAIL);
+    float* sW1s = sB1 + CP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW1s + CP);
+    uint64_t* x_full = bars;            // [2] tx
+    uint64_t* x_ready = bars + 2;       // [2] fix-up warp
+    uint64_t* q_done = bars + 4;        // [2] commit: GEMM1(k) + Q(k) complete -> x stage and the dpre' tile are free
+    uint64_t* g_full = bars + 6;        // [2] tx
+    uint64_t* dw_done = bars + 8;       // [2] commit: dW(k) complete -> dGI stage and the u tile are free
+    uint64_t* du_full = bars + 10;
+    uint64_t* pre_full = bars + 11;
+    uint64_t* dpre_full = bars + 12;    // 16 epilogue warps
+    uint64_t* u_full = bars + 13;       // 16 epilogue warps
+    uint64_t* fin = bars + 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+    copy_image(sW1, a.ws.w1n, W1_BYTES);
+    copy_image(sWT, a.ws.wihT, (TB_NC / 8) * CP * 16);
+    for (int i = tid; i < CP; i += TB_THREADS) { sB1[i] = a.ws.b1f[i]; sW1s[i] = a.ws.w1s[i]; }
+    for (uint32_t i = tid; i < (2 * TB_G_BYTES + A_BYTES) / 16; i += TB_THREADS) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_ready[i], 1); mbar_init(&q_done[i], 1); mbar_init(&g_full[i], 1); mbar_init(&dw_done[i], 1); }
+        mbar_init(du_full, 1); mbar_init(pre_full, 1); mbar_init(dpre_full, 16); mbar_init(u_full, 16); mbar_init(fin, 1);
+        mbar_fence_init();
+        prefetch_tmap(&map128); prefetch_tmap(&map64);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t COL_ACC = 0, COL_QA = 160, COL_QB0 = 320, COL_QB1 = 352, COL_DW0 = 384, COL_DW1 = 448;
+    const int64_t nitems = a.NT * a.T, G = gridDim.x;
+    const int64_t mine = nitems > int64_t(blockIdx.x) ? (nitems - 1 - blockIdx.x) / G + 1 : 0;
+
+    if (warp == 0) {
+        // ===== producer: x stages (TMA) and dGI stages (bulk copy) =====
+        if (IDX || lane == 0)
+            produce_x<2, IDX>(a, &map128, &map64, sX, x_full, mine, G, [&](int64_t k) {
+                // stage k & 1 was last read by GEMM1 / Q of item k - 2; the dGI stage of item k - 1 is requested here too
+                mbar_wait_site(&q_done[k & 1], uint32_t((k >> 1) - 1) & 1u, 21);
+            });
+    } else if (warp == 3) {
+        // ===== dGI producer (its own warp: it must not queue behind the x stage it does not depend on) =====
+        if (lane == 0) {
+            for (int64_t k = 0; k < mine; ++k) {
+                const int g = int(k & 1);
+                if (k >= 2) mbar_wait_site(&dw_done[g], uint32_t((k >> 1) - 1) & 1u, 22);
+                const int64_t item = int64_t(blockIdx.x) + k * G;
+                mbar_expect_tx(&g_full[g], TB_G_BYTES);
+                bulk_g2s(sG + g * TB_G_BYTES, reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * TB_G_BYTES, TB_G_BYTES, &g_full[g]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== UMMA issuer =====
+        if (lane == 0 && mine > 0) {
+            auto issue_du = [&](int64_t k) {
+                mbar_wait_site(&g_full[k & 1], uint32_t(k >> 1) & 1u, 23);
+                tc_fence_after_sync();
+                issue_row_gemm(tmem, COL_ACC, smem_u32(sG + (k & 1) * TB_G_BYTES), smem_u32(sWT), CP, CP, TB_NC / 16);
+                mma_commit(du_full);
+            };
+            issue_du(0);
+            const uint32_t ud = smem_u32(sUD);
+            for (int64_t k = 0; k < mine; ++k) {
+                const int s = int(k & 1);
+                const uint32_t xs = smem_u32(sX + s * XSTAGE), gs = smem_u32(sG + s * TB_G_BYTES);
+                mbar_wait_site(dpre_full, uint32_t(k) & 1u, 24);
+                mbar_wait_site(&x_ready[s], uint32_t(k >> 1) & 1u, 25);
+                tc_fence_after_sync();
+                issue_gemm1_tma(tmem, COL_ACC, xs, smem_u32(sW1));
+                mma_commit(pre_full);
+                const bool acc = k > 0;
+                const uint64_t a_dp = make_smem_desc(ud, 128, kTileChunk);                          // dpre' tile, M block o < 128
+                const uint64_t b_dp = make_smem_desc(ud + 16 * kTileChunk, 128, kTileChunk);        // dpre' tile, columns o >= 128 (N = 32)
+                const uint64_t x128 = make_smem_desc_sw(xs + XB0, 16384, 1024, 2);                  // x columns [0,128)  MN-major, 2 atoms of 64
+                const uint64_t x32 = make_smem_desc_sw(xs + XB2, 8192, 512, 4);                     // x columns [128,160) MN-major, 32-column atom
+                issue_wgrad_desc(tmem + COL_QA, a_dp, 256 >> 4, x128, 2048 >> 4, 128, acc);         // Q[o<128][i<128]
+                issue_wgrad_desc(tmem + COL_QA + 128, a_dp, 256 >> 4, x32, 1024 >> 4, 32, acc);     // Q[o<128][i>=128]
+                issue_wgrad_desc(tmem + COL_QB0, x128, 2048 >> 4, b_dp, 256 >> 4, 32, acc);         // Q[o>=128][i<128]   (transposed: lane = i)
+                issue_wgrad_desc(tmem + COL_QB1, x32, 1024 >> 4, b_dp, 256 >> 4, 32, acc);          // Q[o>=128][i>=128]  (lanes 0..31)
+                mma_commit(&q_done[s]);
+                mbar_wait_site(u_full, uint32_t(k) & 1u, 26);
+                tc_fence_after_sync();
+                if (k + 1 < mine) issue_du(k + 1);
+                const uint64_t a_u0 = make_smem_desc(ud, 128, kTileChunk), a_u1 = make_smem_desc(ud + 16 * kTileChunk, 128, kTileChunk);
+                const uint64_t b_g = make_smem_desc(gs, 128, kTileChunk);
+                issue_wgrad_desc(tmem + COL_DW0, a_u0, 256 >> 4, b_g, 256 >> 4, TB_NC, acc);        // dWih^T[c<128][g]
+                issue_wgrad_desc(tmem + COL_DW1, a_u1, 256 >> 4, b_g, 256 >> 4, TB_NC, acc);        // dWih^T[c>=128][g]  (lanes 0..31; column C = bias)
+                mma_commit(&dw_done[s]);
+            }
+            mma_commit(fin);
+        }
+    } else if (warp == 2) {
+        // ===== LayerNorm columns of the landed x stage: x[:, C] = 1/rstd (-> db1), x[:, C+1] = mean (-> the fold correction) =====
+        for (int64_t k = 0; k < mine; ++k) {
+            const int s = int(k & 1);
+            const int64_t item = int64_t(blockIdx.x) + k * G;
+            float2 st4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st4[i] = a.ws.stats[size_t(item) * TM + 4 * lane + i];
+            mbar_wait_site(&x_full[s], uint32_t(k >> 1) & 1u, 27);
+            unsigned char* xs = sX + s * XSTAGE;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t r = 4 * lane + i;
+                const float inv = 1.f / st4[i].y;
+                // columns C, C+1 = 158, 159: the last 4 bytes of chunk 19 (block 2, chunk 3)
+                *reinterpret_cast<uint32_t*>(xs + XB2 + r * 64u + ((3u ^ ((r >> 1) & 3u)) << 4) + 12u) = pack_bf16(inv, -st4[i].x * inv);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_ready[s]);
+        }
+    } else {
+        // ===== epilogue: thread = (row, part): 40 columns =====
+        const int part = (warp - TB_W_EPI) >> 2;
+        const uint32_t lane_base = uint32_t(warp & 3) * 32u;
+        const int row = int(lane_base) + lane;
+        const int c0 = HALF_COLS * part;
+        auto ld40 = [&](float (&v)[40]) {
+            uint32_t r0[16], r1[16];
+            float r2[8];
+            tmem_ld16_nowait(tmem_addr(tmem, lane_base, COL_ACC + c0), r0);
+            tmem_ld16_nowait(tmem_addr(tmem, lane_base, COL_ACC + c0 + 16), r1);
+            tmem_ld8(tmem_addr(tmem, lane_base, COL_ACC + c0 + 32), r2);          // waits for all three
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { v[e] = __uint_as_float(r0[e]); v[16 + e] = __uint_as_float(r1[e]); }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[32 + e] = r2[e];
+        };
+        unsigned long long mbits = 0ull;
+        float2 st2 = make_float2(0.f, 1.f);
+        if (mine > 0) {
+            mbits = a.ws.mask[size_t(blockIdx.x) * 4 * TM + part * TM + row];
+            st2 = a.ws.stats[size_t(blockIdx.x) * TM + row];
+        }
+        for (int64_t k = 0; k < mine; ++k) {
+            unsigned long long nm = 0ull;
+            float2 nst = make_float2(0.f, 1.f);
+            if (k + 1 < mine) {
+                const int64_t nitem = int64_t(blockIdx.x) + (k + 1) * G;
+                nm = a.ws.mask[size_t(nitem) * 4 * TM + part * TM + row];
+                nst = a.ws.stats[size_t(nitem) * TM + row];
+            }
+            uint4 pk[HALF_CH];
+            {   // ---- dpre' = du * LeakyReLU'(pre) * rstd
+                mbar_wait_site(du_full, uint32_t(k) & 1u, 28);
+                tc_fence_after_sync();
+                float v[40];
+                ld40(v);
+#pragma unroll
+                for (int e = 0; e < 40; ++e) v[e] *= ((mbits >> e) & 1ull) ? st2.y : kLeakySlope * st2.y;
+#pragma unroll
+                for (int ch = 0; ch < HALF_CH; ++ch)
+                    pk[ch] = make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
+                                        pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
+                tc_fence_before_sync();
+                if (k > 0) mbar_wait_site(&dw_done[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u, 29);      // dW(k-1) has read the u tile
+#pragma unroll
+                for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sUD + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dpre_full);
+            }
+            {   // ---- u = LeakyReLU(rstd pre + fold)
+                mbar_wait_site(pre_full, uint32_t(k) & 1u, 30);
+                tc_fence_after_sync();
+                float v[40];
+                ld40(v);
+#pragma unroll
+                for (int e4 = 0; e4 < 10; ++e4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sB1 + c0 + 4 * e4);
+                    const float4 ww = *reinterpret_cast<const float4*>(sW1s + c0 + 4 * e4);
+                    v[4 * e4 + 0] = fmaf(v[4 * e4 + 0], st2.y, fmaf(st2.x, ww.x, bb.x));
+                    v[4 * e4 + 1] = fmaf(v[4 * e4 + 1], st2.y, fmaf(st2.x, ww.y, bb.y));
+                    v[4 * e4 + 2] = fmaf(v[4 * e4 + 2], st2.y, fmaf(st2.x, ww.z, bb.z));
+                    v[4 * e4 + 3] = fmaf(v[4 * e4 + 3], st2.y, fmaf(st2.x, ww.w, bb.w));
+                }
+#pragma unroll
+                for (int ch = 0; ch < HALF_CH; ++ch) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        w[e] = lrelu_pack(v[8 * ch + 2 * e], v[8 * ch + 2 * e + 1]);
+                        const int col = c0 + 8 * ch + 2 * e;
+                        if (col == C) w[e] = 0x3F80u;                               // u[:, C] = 1 (the bias row of dW_ih), zeros beyond
+                        else if (col + 1 == C) w[e] = (w[e] & 0xFFFFu) | 0x3F800000u;
+                        else if (col > C) w[e] = 0u;
+                    }
+                    pk[ch] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                tc_fence_before_sync();
+                mbar_wait_site(&q_done[k & 1], uint32_t(k >> 1) & 1u, 31);                              // Q(k) has read the dpre' tile
+#pragma unroll
+                for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sUD + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(u_full);
+            }
+            mbits = nm; st2 = nst;
+        }
+        if (mine > 0) {
+            // ---- flush the accumulators (raw sums: tc_post subtracts the fold column C+1)
+            mbar_wait_site(fin, 0, 32);
+            tc_fence_after_sync();
+            // QA: lane = o < 128, my 40 columns i
+#pragma unroll 1
+            for (int ch = 0; ch < HALF_CH; ++ch) {
+                float d[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, COL_QA + c0 + ch * 8), d);
+                red_add_v4(a.ws.q + size_t(row) * CP + c0 + ch * 8, d[0], d[1], d[2], d[3]);
+                red_add_v4(a.ws.q + size_t(row) * CP + c0 + ch * 8 + 4, d[4], d[5], d[6], d[7]);
+            }
+            // QB0 / QB1: lane = i (QB1: i = 128 + lane, lanes 0..31), my 8 of the 32 columns o - 128
+            for (int blk = 0; blk < 2; ++blk) {
+                float d[8];
+                tmem_ld8(tmem_addr(tmem, lane_base, (blk == 0 ? COL_QB0 : COL_QB1) + 8 * part), d);
+                const int i = blk * 128 + row;
+                if (i < CP) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int o = 128 + 8 * part + e;
+                        if (o < C) atomicAdd(a.ws.q + size_t(o) * CP + i, d[e]);
+                    }
+                }
+            }
+            // DW0 / DW1: lane = c (DW1: c = 128 + lane), my 16 of the 64 gate columns g -> dwih[g][c]
+            for (int blk = 0; blk < 2; ++blk) {
+                float d[16];
+                tmem_ld16(tmem_addr(tmem, lane_base, (blk == 0 ? COL_DW0 : COL_DW1) + 16 * part), d);
+                const int c = blk * 128 + row;
+                if (c < CP) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) atomicAdd(a.ws.dwih + size_t(16 * part + e) * CP + c, d[e]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -340,9 +680,29 @@ inline bool make_panel_map(CUtensorMap* m, const fvae_panel& x, const FeDims& d,
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x.data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// the resident row table as [rows][C] (pitch row_pitch); box = {box_cols, 1}: what tile::gather4 takes
+inline bool make_table_map(CUtensorMap* m, const fvae_panel& x, const FeDims& d, uint32_t box_cols, CUtensorMapSwizzle sw) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cuuint64_t(d.C), cuuint64_t(x.num_rows)};
+    const cuuint64_t strides[1] = {cuuint64_t(x.row_pitch) * 2};
+    const cuuint32_t box[2] = {box_cols, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x.data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // can this panel take the TMA kernels?  bf16, dense windows, every row 16-byte aligned (pitches multiples of 8 elements)
 inline bool tma_panel_ok(const fvae_panel& x, const FeDims& d) {
-    return x.dtype == FVAE_BF16 && x.row_index == nullptr && d.C > 128 && d.C < CP && (x.row_pitch & 7) == 0 && (x.seq_pitch & 7) == 0 &&
-           (reinterpret_cast<uintptr_t>(x.data) & 15u) == 0 && x.row_pitch >= d.C && x.seq_pitch >= int64_t(d.T - 1) * x.row_pitch + d.C &&
-           get_encode_tiled() != nullptr;
+    if (x.dtype != FVAE_BF16 || d.C <= 128 || d.C + 2 > CP || (x.row_pitch & 7) != 0 || x.row_pitch < d.C ||
+        (reinterpret_cast<uintptr_t>(x.data) & 15u) != 0 || get_encode_tiled() == nullptr || getenv("FVAE_FRONT_CPASYNC"))
+        return false;
+    if (x.row_index) return x.num_rows > 0 && x.num_rows < (int64_t(1) << 31) - 1;
+    return (x.seq_pitch & 7) == 0 && x.seq_pitch >= int64_t(d.T - 1) * x.row_pitch + d.C;
 }
+inline bool make_x_maps(CUtensorMap* m128, CUtensorMap* m64, const fvae_panel& x, const FeDims& d) {
+    if (x.row_index) return make_table_map(m128, x, d, 64, CU_TENSOR_MAP_SWIZZLE_128B) && make_table_map(m64, x, d, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    return make_panel_map(m128, x, d, 64, CU_TENSOR_MAP_SWIZZLE_128B) && make_panel_map(m64, x, d, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+// the fused backward covers NC <= 64 (H <= 20 with the compact gate layout); the forward kernel then saves no xhat tiles
+inline bool tma_fused_backward_ok(const fvae_panel& x, const FeDims& d) { return tma_panel_ok(x, d) && nc_of(d.H) <= TB_NC && !getenv("FVAE_BACK_STREAM"); }
+
