@@ -13,7 +13,7 @@ F32, BF16 = 0, 1
 PREC_FP32, PREC_BF16_TC = 0, 1
 FLAG_TRAIN, FLAG_PHILOX = 1, 2
 FILL_NONE, FILL_FFILL, FILL_FFILL_BFILL = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 SECTIONS = [
     "LN_W", "LN_B", "W1", "B1", "WIH", "WHH", "BIH", "BHH",
@@ -96,6 +96,18 @@ def lib() -> C.CDLL:
     L.fvae_rank_ic.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.fvae_adam_step.restype = C.c_int
     L.fvae_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_float, vp]
+    L.fvae_p2p_buffer_bytes.restype = i64
+    L.fvae_p2p_buffer_bytes.argtypes = [i64, i32]
+    L.fvae_p2p_alloc.restype = C.c_int
+    L.fvae_p2p_alloc.argtypes = [i64, C.POINTER(vp), C.c_char_p]
+    L.fvae_p2p_open.restype = C.c_int
+    L.fvae_p2p_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.fvae_p2p_close.restype = C.c_int
+    L.fvae_p2p_close.argtypes = [vp]
+    L.fvae_p2p_free.restype = C.c_int
+    L.fvae_p2p_free.argtypes = [vp]
+    L.fvae_p2p_allreduce.restype = C.c_int
+    L.fvae_p2p_allreduce.argtypes = [vp, i64, vp, i32, i32, u32, C.c_float, i64, vp]
     if L.fvae_abi_version() != ABI_VERSION:
         raise ImportError("libfvae_b200.so has an unexpected ABI version")
     _lib = L
@@ -104,7 +116,8 @@ def lib() -> C.CDLL:
 
 EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_debug_front_forward", "fvae_debug_noise", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
            "fvae_elbo_forward", "fvae_elbo_backward", "fvae_predict", "fvae_fe_forward", "fvae_fe_backward",
-           "fvae_workspace_latent", "fvae_window_index", "fvae_gather_windows", "fvae_adam_step", "fvae_rank_ic"]
+           "fvae_workspace_latent", "fvae_window_index", "fvae_gather_windows", "fvae_adam_step", "fvae_rank_ic",
+           "fvae_p2p_buffer_bytes", "fvae_p2p_alloc", "fvae_p2p_open", "fvae_p2p_close", "fvae_p2p_free", "fvae_p2p_allreduce"]
 
 
 class FvaeError(RuntimeError):

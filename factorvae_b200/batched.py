@@ -29,9 +29,27 @@ def shard_dates(B: int, world: int, rank: int) -> Tuple[int, int]:
 
 class DateShardedStep:
     def __init__(self, layout: engine.ParamLayout, flat: torch.Tensor, precision: str = "bf16", group=None,
-                 seed: int = 42):
+                 seed: int = 42, collective: str = "auto"):
+        """collective: "p2p" = the one-kernel all-reduce over NVLink peer memory (p2p.P2PAllReduce), "nccl" = one
+        torch.distributed all-reduce, "auto" = p2p when the group runs NCCL on GPUs with peer access, else nccl."""
         self.layout, self.flat, self.precision, self.group, self.seed = layout, flat, precision, group, seed
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.p2p = None
+        if self.world > 1 and collective in ("auto", "p2p") and flat.is_cuda and dist.get_backend(group) == "nccl":
+            try:
+                from .p2p import P2PAllReduce
+                self.p2p = P2PAllReduce(layout.total + 4, flat.device, group)
+            except Exception:
+                if collective == "p2p":
+                    raise
+                self.p2p = None
+            # all ranks must agree (a rank without peer access would wait for an NCCL call the others never issue)
+            ok = torch.tensor([1 if self.p2p is not None else 0], device=flat.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                if self.p2p is not None:
+                    self.p2p.close()
+                self.p2p = None
         # gradient buffer with a 4-float tail: [total] = loss (written by the kernels), rest padding
         self.gradbuf = torch.zeros(layout.total + 4, dtype=torch.float32, device=flat.device)
         self.workspace: Optional[torch.Tensor] = None
@@ -58,7 +76,9 @@ class DateShardedStep:
 
     def _reduce(self, buf: torch.Tensor, local_weight: float) -> None:
         """The single gradient exchange of the step: buf <- sum over ranks of local_weight * buf (loss in the tail)."""
-        if self.world > 1:
+        if self.world > 1 and self.p2p is not None:
+            self.p2p.all_reduce(buf, local_weight)
+        elif self.world > 1:
             if abs(local_weight * self.world - 1.0) < 1e-12 and dist.get_backend(self.group) == "nccl":
                 dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
             else:

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfvae_b200.so")
-SOURCES = ["fvae_abi.cu", "heads.cu", "heads_tc.cu", "fe_f32.cu", "fe_tc.cu", "panel.cu", "optim.cu", "metrics.cu", "noise.cu"]
+SOURCES = ["fvae_abi.cu", "heads.cu", "heads_tc.cu", "fe_f32.cu", "fe_tc.cu", "panel.cu", "optim.cu", "metrics.cu", "noise.cu", "p2p.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

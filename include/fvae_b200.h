@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FVAE_ABI_VERSION 3
+#define FVAE_ABI_VERSION 4
 
 /* status codes (<0: argument errors) */
 #define FVAE_OK 0
@@ -199,6 +199,20 @@ int fvae_gather_windows(const fvae_panel* panel, int64_t S, int32_t T, int32_t C
 int fvae_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                    void* stream);
+
+/* ---- the step's single collective, as one kernel over NVLink peer memory (the reference has no data parallelism:
+ *      no counterpart).  Each rank allocates a communication buffer (fvae_p2p_alloc: cudaMalloc + IPC handle), the ranks
+ *      exchange the 64-byte handles (host side, e.g. torch.distributed.all_gather_object) and map each other's buffers
+ *      (fvae_p2p_open).  fvae_p2p_allreduce: inout[n] <- scale * sum_ranks inout[n], one launch: push to every peer's slot,
+ *      publish per-chunk flags, wait for the peers' chunks, sum in rank order (bit-identical on all ranks).  `epoch` = 1, 2,
+ *      3, ... the same on every rank; `peer_bases` is a DEVICE array of the world's buffer addresses as mapped here.        */
+int64_t fvae_p2p_buffer_bytes(int64_t n, int32_t world);
+int fvae_p2p_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
+int fvae_p2p_open(const unsigned char* handle64, void** dev_ptr);
+int fvae_p2p_close(void* dev_ptr);
+int fvae_p2p_free(void* dev_ptr);
+int fvae_p2p_allreduce(float* inout, int64_t n, void* const* peer_bases, int32_t world, int32_t rank, uint32_t epoch, float scale,
+                       int64_t n_alloc, void* stream);
 
 /* ---- evaluation metric: per-date Spearman rank correlation of predictions and labels (replaces the
  *      per-date pandas .rank() + scipy.stats.spearmanr loop of utils.py:113-129).  ric[d] for the dates of

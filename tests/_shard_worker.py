@@ -48,11 +48,23 @@ def main():
     d0, d1 = shard_dates(B, world, rank)
     ptr = torch.tensor([0] + list(torch.tensor(counts[d0:d1]).cumsum(0)), dtype=torch.int32, device=dev)
     base = sum(counts[:d0])
-    st = DateShardedStep(L, flat, precision=precision, seed=11)
-    out, _ = st.step(torch.cat(xs[d0:d1]), torch.cat(ys[d0:d1]), ptr, global_dates=B, unit_base=base, train=True)
+    st = DateShardedStep(L, flat, precision=precision, seed=11, collective="p2p")     # the one-kernel NVLink all-reduce
+    for _ in range(3):                               # several epochs through the double-buffered slots
+        st.step_index = 0
+        out, _ = st.step(torch.cat(xs[d0:d1]), torch.cat(ys[d0:d1]), ptr, global_dates=B, unit_base=base, train=True)
     torch.cuda.synchronize()
     g_all = st.grad.clone()
     loss_all = float(st.loss.item())
+    # the same step through NCCL: the two collectives must agree (both sum the same shard gradients)
+    st2 = DateShardedStep(L, flat, precision=precision, seed=11, collective="nccl")
+    st2.step(torch.cat(xs[d0:d1]), torch.cat(ys[d0:d1]), ptr, global_dates=B, unit_base=base, train=True)
+    torch.cuda.synchronize()
+    d_coll = float((st2.grad.double() - g_all.double()).norm() / g_all.double().norm())
+    # bit-identical on every rank (rank-ordered sum): compare a checksum of the bytes across ranks
+    chk = g_all.view(torch.int32).to(torch.int64).sum().reshape(1)
+    lo_, hi_ = chk.clone(), chk.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    same_everywhere = bool((lo_ == hi_).item())
     ok = True
     if rank == 0:
         solo = DateShardedStep(L, flat, precision=precision, group=None, seed=11)
@@ -67,8 +79,9 @@ def main():
         n0 = sum(counts[d0:d1])
         same = torch.equal(out["yhat"], o1["yhat"][base:base + n0]) and torch.equal(out["mu_y"], o1["mu_y"][base:base + n0])
         print(f"G={world} {precision}: grad rel-L2 {rel:.3e} max-rel {mx:.3e}; loss {loss_all:.7f} vs {l1:.7f} (rel {lrel:.2e}); "
-              f"per-unit outputs bit-identical: {same}", flush=True)
-        ok = rel <= 2e-6 and mx <= 2e-5 and lrel <= 1e-6 and same
+              f"per-unit outputs bit-identical: {same}; p2p vs nccl rel-L2 {d_coll:.2e}; p2p result identical on all ranks: "
+              f"{same_everywhere}; p2p active: {st.p2p is not None}", flush=True)
+        ok = rel <= 2e-6 and mx <= 2e-5 and lrel <= 1e-6 and same and d_coll <= 2e-6 and same_everywhere and st.p2p is not None
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -19,7 +19,7 @@ def cabi():
 
 def test_library_exports_every_declared_symbol(cabi):
     hdr = open(os.path.join(ROOT, "include", "fvae_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(fvae_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(fvae_[a-z0-9_]+)\s*\(", hdr)))
     assert len(declared) >= 11
     lib = C.CDLL(cabi.LIB_PATH)
     for name in declared:
