@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int C = a.C;
+    const int C = a.C, NC = a.NC;
+    const uint32_t g_bytes = uint32_t(NC / 8) * TILE_CH;                   // the dGI tile of one item (NC <= 64 gate columns)
     unsigned char* sX = smem;
     unsigned char* sG = smem + TB_OFF_G;
     unsigned char* sUD = smem + TB_OFF_UD;
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     copy_image(sW1, a.ws.w1n, W1_BYTES);
-    copy_image(sWT, a.ws.wihT, (TB_NC / 8) * CP * 16);
+    copy_image(sWT, a.ws.wihT, uint32_t(NC / 8) * CP * 16);
     for (int i = tid; i < CP; i += TB_THREADS) { sB1[i] = a.ws.b1f[i]; sW1s[i] = a.ws.w1s[i]; }
     for (uint32_t i = tid; i < (2 * TB_G_BYTES + A_BYTES) / 16; i += TB_THREADS) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -458,8 +459,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 const int g = int(k & 1);
                 if (k >= 2) mbar_wait_site(&dw_done[g], uint32_t((k >> 1) - 1) & 1u, 22);
                 const int64_t item = int64_t(blockIdx.x) + k * G;
-                mbar_expect_tx(&g_full[g], TB_G_BYTES);
-                bulk_g2s(sG + g * TB_G_BYTES, reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * TB_G_BYTES, TB_G_BYTES, &g_full[g]);
+                mbar_expect_tx(&g_full[g], g_bytes);
+                bulk_g2s(sG + g * TB_G_BYTES, reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * g_bytes, g_bytes, &g_full[g]);
             }
         }
     } else if (warp == 1) {
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
             auto issue_du = [&](int64_t k) {
                 mbar_wait_site(&g_full[k & 1], uint32_t(k >> 1) & 1u, 23);
                 tc_fence_after_sync();
-                issue_row_gemm(tmem, COL_ACC, smem_u32(sG + (k & 1) * TB_G_BYTES), smem_u32(sWT), CP, CP, TB_NC / 16);
+                issue_row_gemm(tmem, COL_ACC, smem_u32(sG + (k & 1) * TB_G_BYTES), smem_u32(sWT), CP, CP, NC / 16);
                 mma_commit(du_full);
             };
             issue_du(0);
@@ -496,8 +497,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 if (k + 1 < mine) issue_du(k + 1);
                 const uint64_t a_u0 = make_smem_desc(ud, 128, kTileChunk), a_u1 = make_smem_desc(ud + 16 * kTileChunk, 128, kTileChunk);
                 const uint64_t b_g = make_smem_desc(gs, 128, kTileChunk);
-                issue_wgrad_desc(tmem + COL_DW0, a_u0, 256 >> 4, b_g, 256 >> 4, TB_NC, acc);        // dWih^T[c<128][g]
-                issue_wgrad_desc(tmem + COL_DW1, a_u1, 256 >> 4, b_g, 256 >> 4, TB_NC, acc);        // dWih^T[c>=128][g]  (lanes 0..31; column C = bias)
+                issue_wgrad_desc(tmem + COL_DW0, a_u0, 256 >> 4, b_g, 256 >> 4, uint32_t(NC), acc);  // dWih^T[c<128][g]
+                issue_wgrad_desc(tmem + COL_DW1, a_u1, 256 >> 4, b_g, 256 >> 4, uint32_t(NC), acc);  // dWih^T[c>=128][g]  (lanes 0..31; column C = bias)
                 mma_commit(&dw_done[s]);
             }
             mma_commit(fin);
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 const int c = blk * 128 + row;
                 if (c < CP) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) atomicAdd(a.ws.dwih + size_t(16 * part + e) * CP + c, d[e]);
+                    for (int e = 0; e < 16; ++e) if (16 * part + e < NC) atomicAdd(a.ws.dwih + size_t(16 * part + e) * CP + c, d[e]);
                 }
             }
         }

@@ -61,7 +61,9 @@ def main():
     B, N, T, H, K, M = min(wl["B"], wl["micro"]), wl["N"], wl["T"], wl["H"], wl["K"], wl["M"]
     layout = engine.ParamLayout(bench.C_FEATURES, H, K, M)
     flat = layout.pack(bench.build_params(H, K, M), dev)
-    x = torch.randn(B * N, T, bench.C_FEATURES, device=dev).clamp_(-3, 3).to(torch.bfloat16)
+    store = torch.zeros(B * N, T, 160, device=dev, dtype=torch.bfloat16)
+    store[:, :, :bench.C_FEATURES] = torch.randn(B * N, T, bench.C_FEATURES, device=dev).clamp_(-3, 3).to(torch.bfloat16)
+    x = store[:, :, :bench.C_FEATURES]
     y = torch.randn(B * N, device=dev)
     ptr = engine.uniform_date_ptr(B, N, dev)
     st = DateShardedStep(layout, flat, precision="bf16", seed=42)
