@@ -142,7 +142,7 @@ __global__ void tc_prep_kernel(PrepArgs a) {
     for (int idx = tid; idx < CP * CP; idx += nth) {
         const int n = idx / CP, k = idx % CP;
         const float wv = (n < C && k < C) ? a.W1[n * C + k] * a.ln_w[k] : 0.f;
-        put_img(a.ws.w1n, CP, n, k, wv);         // no bias column: the TMA kernels add b1f in the epilogue
+        if (k != C && k != C + 1) put_img(a.ws.w1n, CP, n, k, wv);     // rows C, C+1 of the TMA image: the LayerNorm fold (written below)
         if (k == C) continue;                    // column C carries the folded bias (written below by another thread)
         put_img(a.ws.w1g, CP, n, k, wv);
     }
@@ -183,7 +183,12 @@ __global__ void tc_prep_kernel(PrepArgs a) {
             for (int k = part; k < C; k += 8) ws_ += __bfloat162float(__float2bfloat16(a.W1[n * C + k] * a.ln_w[k]));
 #pragma unroll
         for (int s = 4; s > 0; s >>= 1) ws_ += __shfl_xor_sync(0xffffffffu, ws_, s);
-        if (part == 0) a.ws.w1s[n] = ws_;
+        if (part == 0) {
+            a.ws.w1s[n] = ws_;
+            // TMA kernels: the x stage carries (1/rstd, mean) in columns C, C+1, so acc = x.W1g + b1f / rstd - mean w1s = pre / rstd
+            put_img(a.ws.w1n, CP, n, C, n < C ? v : 0.f);
+            put_img(a.ws.w1n, CP, n, C + 1, n < C ? -ws_ : 0.f);
+        }
     }
     for (int col = tid; col < NC; col += nth) {
         int gate, j;
@@ -730,7 +735,7 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
     if (tma_panel_ok(x, d)) {
         CUtensorMap m128, m64;
         if (make_x_maps(&m128, &m64, x, d)) {
-            TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), ws};
+            TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? 1 : 0, ws};
             const size_t fixed = A_BYTES + W1_BYTES + size_t(KCH) * NC * 16 + 2 * CP * 4 + 4 * TM * 8 + 256 + 1024;
             const int xst = (fixed + 2 * XSTAGE <= kMaxSmem) ? 2 : 1;
             const int ngi = (320 + 2 * NC <= 512) ? 2 : 1;
@@ -815,7 +820,7 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         // one fused kernel: raw x rows (TMA) + dGI tiles (bulk copies) read once; GEMM1 recomputed; Q and dW_ih accumulated in TMEM
         CUtensorMap m128, m64;
         if (!make_x_maps(&m128, &m64, x, d)) return FVAE_ERR_UNSUPPORTED;
-        TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), ws};
+        TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? 1 : 0, ws};
         cudaError_t ce2;
         if (x.row_index) {
             if ((ce2 = cudaFuncSetAttribute(tc_back_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TB_SMEM))) != cudaSuccess) return int(ce2);

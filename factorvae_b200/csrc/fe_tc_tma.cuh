@@ -18,16 +18,21 @@
 //      the box are out of bounds and arrive as zeros whatever the padding holds.  Dense pitch-158 panels keep the cp.async path.
 //
 // Roles (576 threads, one CTA per SM, persistent over items; every hand-off is an mbarrier, no CTA barrier in steady state):
-//   warp 0      producer   : three tensor-map loads per item (2 x [128 x 64] SWIZZLE_128B + [128 x 32] SWIZZLE_64B = 40 KB)
-//   warp 1      UMMA issuer: GEMM1(k+1) is queued in front of GEMM2(k); two accumulator sets for pre, one or two for GI
-//   warps 2-5   row statistics: thread = row, reads its 158 features from the swizzled stage (conflict-free), mean / rstd
-//   warps 6-13  u epilogue : thread = (row, 80 columns): pre -> LayerNorm fold -> LeakyReLU -> bf16 u tile (A of GEMM2)
-//   warps 14-17 GI epilogue: thread = row: accumulator + bias (folded in column C) -> bf16 GI tile in HBM
+//   warps 0-3   row statistics: thread = row, reads its 158 features from the swizzled stage (conflict-free), mean / rstd;
+//               writes (1/rstd, mean) into columns C, C+1 of the stage: rows C, C+1 of the W1n image hold (b1f, -w1s), so the
+//               accumulator is pre / rstd and the whole LayerNorm fold costs the epilogue ONE multiply per element
+//   warps 4-11  u epilogue : thread = (row, 80 columns): u = rstd LeakyReLU(acc) -> bf16 u tile (A of GEMM2)
+//   warps 12-15 GI epilogue: thread = row: accumulator (bias folded in column C) -> bf16 GI tile in HBM
+//   warp 16     producer   : three tensor-map loads per item (2 x [128 x 64] SWIZZLE_128B + [128 x 32] SWIZZLE_64B = 40 KB)
+//   warp 17     UMMA issuer: GEMM1(k+1) is queued in front of GEMM2(k); two accumulator sets for pre, one or two for GI
 #pragma once
 #include <cuda.h>
 
 constexpr int TF_THREADS = 576;
-constexpr int TF_W_STAT = 2, TF_W_EPU = 6, TF_W_EPG = 14;      // first warp of each role
+// Warp ids matter: a scheduler picks the HIGHEST warp id among its eligible warps, so the two single-thread roles every
+// other warp waits for (UMMA issue, TMA issue) sit in the last warps; an issuer in warp 1 starves behind the epilogue warps
+// of its scheduler (measured: 42 UMMAs took 3.2 k cycles to issue).
+constexpr int TF_W_STAT = 0, TF_W_EPU = 4, TF_W_EPG = 12, TF_W_PROD = 16, TF_W_MMA = 17;      // first warp of each role
 constexpr uint32_t XB0 = 0, XB1 = 16384, XB2 = 32768;          // x stage: [128][128B] sw128 | [128][128B] sw128 | [128][64B] sw64
 constexpr uint32_t XSTAGE = 40960;
 
@@ -38,6 +43,7 @@ struct TmaFrontArgs {
     int S;
     const int32_t* row_index;     // resident panel: [S][T] rows of the table (NULL: dense windows)
     int32_t oob_row;              // a row number past the table: gathered as zeros (sequences beyond S)
+    int32_t timeline;             // diagnostics (FVAE_TIMELINE=1): CTA 0 records clock64() at every hand-off into ws.xh and prints the table
     TcWs ws;
 };
 
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
         mbar_fence_init();
         prefetch_tmap(&map128); prefetch_tmap(&map64);
     }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (warp == TF_W_MMA) tmem_alloc<512>(tmem_slot);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -205,18 +211,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
     const int64_t nitems = a.NT * a.T, G = gridDim.x;
     const int64_t mine = nitems > int64_t(blockIdx.x) ? (nitems - 1 - blockIdx.x) / G + 1 : 0;
 
-    if (warp == 0) {
+    if (warp == TF_W_PROD) {
         // ===== producer =====
         if (IDX || lane == 0)
             produce_x<XST, IDX>(a, &map128, &map64, sX, x_full, mine, G,
                                 [&](int64_t k) { mbar_wait_site(&x_empty[k % XST], uint32_t((k / XST) - 1) & 1u, 1); });
-    } else if (warp == 1) {
+    } else if (warp == TF_W_MMA) {
         // ===== UMMA issuer =====
         if (lane == 0 && mine > 0) {
             auto gemm1 = [&](int64_t k) {
                 const int s = int(k % XST), b = int(k & 1);
                 if (k >= 2) mbar_wait_site(&pre_empty[b], uint32_t((k >> 1) - 1) & 1u, 2);
-                mbar_wait_site(&x_full[s], uint32_t(k / XST) & 1u, 3);
+                mbar_wait_site(&st_full[k & 3], uint32_t(k >> 2) & 1u, 3);       // landed AND columns C, C+1 = (1/rstd, mean) written
                 tc_fence_after_sync();
                 issue_gemm1_tma(tmem, COL_PRE + uint32_t(b) * CP, smem_u32(sX + s * XSTAGE), smem_u32(sW1));
                 mma_commit(&pre_full[b]);
@@ -244,6 +250,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
             float mean, rstd;
             row_stats(xs, row, C, mean, rstd);
             sStat[q * TM + row] = make_float2(-mean * rstd, rstd);
+            // columns C, C+1 of the stage (the last 4 bytes of chunk 19): they meet rows (b1f, -w1s) of the W1n image
+            *reinterpret_cast<uint32_t*>(const_cast<unsigned char*>(xs) + XB2 + uint32_t(row) * 64u + ((3u ^ ((uint32_t(row) >> 1) & 3u)) << 4) + 12u) =
+                pack_bf16(1.f / rstd, mean);
+            fence_async_smem();
             const int64_t item = int64_t(blockIdx.x) + k * G;
             a.ws.stats[size_t(item) * TM + row] = make_float2(-mean * rstd, rstd);     // saved for the fused backward
             if (SAVE_XH) {       // the normalised tile (column C = 1) for the streaming backward kernels
@@ -286,24 +296,15 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
                 float v[16];
                 tmem_ld16(tmem_addr(tmem, lane_base, COL_PRE + uint32_t(b) * CP + c0 + gq * 16), v);
 #pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(sB1 + c0 + gq * 16 + 4 * e4);
-                    const float4 ww = *reinterpret_cast<const float4*>(sW1s + c0 + gq * 16 + 4 * e4);
-                    v[4 * e4 + 0] = fmaf(v[4 * e4 + 0], st2.y, fmaf(st2.x, ww.x, bb.x));
-                    v[4 * e4 + 1] = fmaf(v[4 * e4 + 1], st2.y, fmaf(st2.x, ww.y, bb.y));
-                    v[4 * e4 + 2] = fmaf(v[4 * e4 + 2], st2.y, fmaf(st2.x, ww.z, bb.z));
-                    v[4 * e4 + 3] = fmaf(v[4 * e4 + 3], st2.y, fmaf(st2.x, ww.w, bb.w));
-                }
-#pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const int cc = gq * 16 + e;
                     if (v[e] > 0.f) { if (cc < 40) mlo |= 1ull << cc; else mhi |= 1ull << (cc - 40); }
                 }
                 uint32_t w[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) w[e] = lrelu_pack(v[2 * e], v[2 * e + 1]);
+                for (int e = 0; e < 8; ++e) w[e] = lrelu_pack(v[2 * e] * st2.y, v[2 * e + 1] * st2.y);      // rstd > 0: rstd lrelu(a) = lrelu(rstd a)
                 // the ones column (u[:, C] = 1: the GI bias rides in column C of the W_ih image), zeros beyond
-                if (c0 + gq * 16 + 16 > C) {
+                if (c0 + gq * 16 + 16 > C) {                       // warp-uniform: the last 16-column group of the upper half only
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int col = c0 + gq * 16 + 2 * e;
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(u_full);
         }
-    } else {
+    } else if (warp < TF_W_PROD) {
         // ===== GI epilogue: thread = row =====
         const uint32_t lane_base = uint32_t(warp & 3) * 32u;
         const int row = int(lane_base) + lane;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<512>(tmem);
+    if (warp == TF_W_MMA) tmem_dealloc<512>(tmem);
 }
 
 // ---- fused front backward (TMA form, NC <= 64) -------------------------------------------------------------------------
@@ -377,10 +378,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
 // until dW(k) has | W1n image 50 KB | W_ih^T image 20 KB.
 // Per item the tensor pipe runs  du(k) . [E: dpre'] . GEMM1(k), Q(k) . [E: u, under Q] . du(k+1), dW(k) ...  -- 2.6 k cycles of
 // MMA per item against 2 x 0.6 k of epilogue on the critical path.
-// Roles (640 threads): warp 0 producer, warp 1 UMMA issuer, warp 2 writes the two LayerNorm columns (1/rstd, mean) into the
-// landed x stage, warps 4-19 epilogue: thread = (row, 40 columns).
+// Roles (640 threads): warps 0-15 epilogue, thread = (row, 40 columns); warp 16 writes the two LayerNorm columns (1/rstd, mean)
+// into the landed x stage; warp 17 dGI producer; warp 18 x producer; warp 19 UMMA issuer.
 constexpr int TB_THREADS = 640;
-constexpr int TB_W_EPI = 4;
+constexpr int TB_W_EPI = 0, TB_W_FIX = 16, TB_W_GPROD = 17, TB_W_XPROD = 18, TB_W_MMA = 19;   // issuers last: highest warp id wins the scheduler
 constexpr int TB_NC = 64;
 constexpr uint32_t TB_G_BYTES = (TB_NC / 8) * TILE_CH;            // 16384
 constexpr uint32_t TB_OFF_G = 2 * XSTAGE, TB_OFF_UD = TB_OFF_G + 2 * TB_G_BYTES, TB_OFF_W1 = TB_OFF_UD + A_BYTES,
@@ -396,6 +397,9 @@ __device__ __forceinline__ void issue_wgrad_desc(uint32_t tmem_col, uint64_t ad,
         ad += astep; bd += bstep;
     }
 }
+
+// diagnostics: event e of item k of CTA 0 (16 events per item)
+#define TL(e) do { if (tl) tl[size_t(k) * 16 + (e)] = clock64(); } while (0)
 
 template <bool IDX>
 __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid_constant__ CUtensorMap map128,
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
         mbar_fence_init();
         prefetch_tmap(&map128); prefetch_tmap(&map64);
     }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (warp == TB_W_MMA) tmem_alloc<512>(tmem_slot);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -444,15 +448,16 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
     constexpr uint32_t COL_ACC = 0, COL_QA = 160, COL_QB0 = 320, COL_QB1 = 352, COL_DW0 = 384, COL_DW1 = 448;
     const int64_t nitems = a.NT * a.T, G = gridDim.x;
     const int64_t mine = nitems > int64_t(blockIdx.x) ? (nitems - 1 - blockIdx.x) / G + 1 : 0;
+    unsigned long long* tl = (a.timeline && blockIdx.x == 0 && lane == 0) ? reinterpret_cast<unsigned long long*>(a.ws.xh) : nullptr;
 
-    if (warp == 0) {
-        // ===== producer: x stages (TMA) and dGI stages (bulk copy) =====
+    if (warp == TB_W_XPROD) {
+        // ===== producer: x stages (TMA) =====
         if (IDX || lane == 0)
             produce_x<2, IDX>(a, &map128, &map64, sX, x_full, mine, G, [&](int64_t k) {
                 // stage k & 1 was last read by GEMM1 / Q of item k - 2; the dGI stage of item k - 1 is requested here too
                 mbar_wait_site(&q_done[k & 1], uint32_t((k >> 1) - 1) & 1u, 21);
             });
-    } else if (warp == 3) {
+    } else if (warp == TB_W_GPROD) {
         // ===== dGI producer (its own warp: it must not queue behind the x stage it does not depend on) =====
         if (lane == 0) {
             for (int64_t k = 0; k < mine; ++k) {
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 bulk_g2s(sG + g * TB_G_BYTES, reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * g_bytes, g_bytes, &g_full[g]);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == TB_W_MMA) {
         // ===== UMMA issuer =====
         if (lane == 0 && mine > 0) {
             auto issue_du = [&](int64_t k) {
@@ -477,8 +482,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
             for (int64_t k = 0; k < mine; ++k) {
                 const int s = int(k & 1);
                 const uint32_t xs = smem_u32(sX + s * XSTAGE), gs = smem_u32(sG + s * TB_G_BYTES);
+                TL(0);
                 mbar_wait_site(dpre_full, uint32_t(k) & 1u, 24);
+                TL(1);
                 mbar_wait_site(&x_ready[s], uint32_t(k >> 1) & 1u, 25);
+                TL(2);
                 tc_fence_after_sync();
                 issue_gemm1_tma(tmem, COL_ACC, xs, smem_u32(sW1));
                 mma_commit(pre_full);
@@ -492,18 +500,22 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 issue_wgrad_desc(tmem + COL_QB0, x128, 2048 >> 4, b_dp, 256 >> 4, 32, acc);         // Q[o>=128][i<128]   (transposed: lane = i)
                 issue_wgrad_desc(tmem + COL_QB1, x32, 1024 >> 4, b_dp, 256 >> 4, 32, acc);          // Q[o>=128][i>=128]  (lanes 0..31)
                 mma_commit(&q_done[s]);
+                TL(3);
                 mbar_wait_site(u_full, uint32_t(k) & 1u, 26);
+                TL(4);
                 tc_fence_after_sync();
                 if (k + 1 < mine) issue_du(k + 1);
+                TL(5);
                 const uint64_t a_u0 = make_smem_desc(ud, 128, kTileChunk), a_u1 = make_smem_desc(ud + 16 * kTileChunk, 128, kTileChunk);
                 const uint64_t b_g = make_smem_desc(gs, 128, kTileChunk);
                 issue_wgrad_desc(tmem + COL_DW0, a_u0, 256 >> 4, b_g, 256 >> 4, uint32_t(NC), acc);  // dWih^T[c<128][g]
                 issue_wgrad_desc(tmem + COL_DW1, a_u1, 256 >> 4, b_g, 256 >> 4, uint32_t(NC), acc);  // dWih^T[c>=128][g]  (lanes 0..31; column C = bias)
                 mma_commit(&dw_done[s]);
+                TL(6);
             }
             mma_commit(fin);
         }
-    } else if (warp == 2) {
+    } else if (warp == TB_W_FIX) {
         // ===== LayerNorm columns of the landed x stage: x[:, C] = 1/rstd (-> db1), x[:, C+1] = mean (-> the fold correction) =====
         for (int64_t k = 0; k < mine; ++k) {
             const int s = int(k & 1);
@@ -541,6 +553,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[32 + e] = r2[e];
         };
+        if (warp != TB_W_EPI) tl = nullptr;
         unsigned long long mbits = 0ull;
         float2 st2 = make_float2(0.f, 1.f);
         if (mine > 0) {
@@ -557,58 +570,64 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
             }
             uint4 pk[HALF_CH];
             {   // ---- dpre' = du * LeakyReLU'(pre) * rstd
+                TL(7);
                 mbar_wait_site(du_full, uint32_t(k) & 1u, 28);
+                TL(8);
                 tc_fence_after_sync();
                 float v[40];
                 ld40(v);
+                const uint32_t mlo = uint32_t(mbits), mhi = uint32_t(mbits >> 32);
+                const float s_pos = st2.y, s_neg = kLeakySlope * st2.y;
 #pragma unroll
-                for (int e = 0; e < 40; ++e) v[e] *= ((mbits >> e) & 1ull) ? st2.y : kLeakySlope * st2.y;
+                for (int e = 0; e < 40; ++e) v[e] *= ((e < 32 ? mlo >> e : mhi >> (e - 32)) & 1u) ? s_pos : s_neg;
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch)
                     pk[ch] = make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
                                         pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
                 tc_fence_before_sync();
+                TL(9);
                 if (k > 0) mbar_wait_site(&dw_done[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u, 29);      // dW(k-1) has read the u tile
+                TL(10);
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sUD + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(dpre_full);
+                TL(11);
             }
             {   // ---- u = LeakyReLU(rstd pre + fold)
                 mbar_wait_site(pre_full, uint32_t(k) & 1u, 30);
+                TL(12);
                 tc_fence_after_sync();
                 float v[40];
                 ld40(v);
-#pragma unroll
-                for (int e4 = 0; e4 < 10; ++e4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(sB1 + c0 + 4 * e4);
-                    const float4 ww = *reinterpret_cast<const float4*>(sW1s + c0 + 4 * e4);
-                    v[4 * e4 + 0] = fmaf(v[4 * e4 + 0], st2.y, fmaf(st2.x, ww.x, bb.x));
-                    v[4 * e4 + 1] = fmaf(v[4 * e4 + 1], st2.y, fmaf(st2.x, ww.y, bb.y));
-                    v[4 * e4 + 2] = fmaf(v[4 * e4 + 2], st2.y, fmaf(st2.x, ww.z, bb.z));
-                    v[4 * e4 + 3] = fmaf(v[4 * e4 + 3], st2.y, fmaf(st2.x, ww.w, bb.w));
-                }
+                const int one_ch = (C >= c0 && C < c0 + HALF_COLS) ? (C - c0) >> 3 : -1;               // warp-uniform: my chunk that holds column C
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch) {
                     uint32_t w[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        w[e] = lrelu_pack(v[8 * ch + 2 * e], v[8 * ch + 2 * e + 1]);
-                        const int col = c0 + 8 * ch + 2 * e;
-                        if (col == C) w[e] = 0x3F80u;                               // u[:, C] = 1 (the bias row of dW_ih), zeros beyond
-                        else if (col + 1 == C) w[e] = (w[e] & 0xFFFFu) | 0x3F800000u;
-                        else if (col > C) w[e] = 0u;
+                    for (int e = 0; e < 4; ++e) w[e] = lrelu_pack(v[8 * ch + 2 * e] * st2.y, v[8 * ch + 2 * e + 1] * st2.y);   // rstd lrelu(acc)
+                    if (ch == one_ch) {                                      // u[:, C] = 1 (the bias row of dW_ih), zeros beyond
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = c0 + 8 * ch + 2 * e;
+                            if (col == C) w[e] = 0x3F80u;
+                            else if (col + 1 == C) w[e] = (w[e] & 0xFFFFu) | 0x3F800000u;
+                            else if (col > C) w[e] = 0u;
+                        }
                     }
                     pk[ch] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 tc_fence_before_sync();
+                TL(13);
                 mbar_wait_site(&q_done[k & 1], uint32_t(k >> 1) & 1u, 31);                              // Q(k) has read the dpre' tile
+                TL(14);
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sUD + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(u_full);
+                TL(15);
             }
             mbits = nm; st2 = nst;
         }
@@ -651,8 +670,21 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<512>(tmem);
+    if (warp == TB_W_MMA) tmem_dealloc<512>(tmem);
+    if (a.timeline && blockIdx.x == 0 && tid == 0) {
+        __threadfence();
+        const unsigned long long* t = reinterpret_cast<const unsigned long long*>(a.ws.xh);
+        const int64_t n = mine < 24 ? mine : 24;
+        printf("fvae timeline (CTA 0, cycles relative to item start = MMA waits dpre): MMA: dpre_full x_ready q_issued u_full du_next dw_issued | EPI: du_wait du_full dpre_done dwdone_seen dpre_arrive pre_full u_done qdone_seen u_arrive\n");
+        for (int64_t k = 0; k < n; ++k) {
+            const unsigned long long t0 = t[k * 16];
+            printf("item %2d:", int(k));
+            for (int e = 1; e < 16; ++e) printf(" %6lld", (long long)(t[k * 16 + e] - t0));
+            printf("  | next item starts +%lld\n", (long long)(t[(k + 1) * 16] - t0));
+        }
+    }
 }
+#undef TL
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
