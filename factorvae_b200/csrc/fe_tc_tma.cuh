@@ -130,7 +130,7 @@ __device__ __forceinline__ void issue_gemm1_tma(uint32_t tmem, uint32_t dcol, ui
         if (ks < 4) ad = make_smem_desc_sw(xs + XB0 + ks * 32, 16, 1024, 2);
         else if (ks < 8) ad = make_smem_desc_sw(xs + XB1 + (ks - 4) * 32, 16, 1024, 2);
         else ad = make_smem_desc_sw(xs + XB2 + (ks - 8) * 32, 16, 512, 4);
-        mma_bf16_ss(tmem + dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        mma_bf16_ss_w(tmem + dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
         bd += bstep;
     }
 }
@@ -215,18 +215,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
         // ===== producer =====
         if (IDX || lane == 0)
             produce_x<XST, IDX>(a, &map128, &map64, sX, x_full, mine, G,
-                                [&](int64_t k) { mbar_wait_site(&x_empty[k % XST], uint32_t((k / XST) - 1) & 1u, 1); });
+                                [&](int64_t k) { mbar_wait_relaxed(&x_empty[k % XST], uint32_t((k / XST) - 1) & 1u, 1); });
     } else if (warp == TF_W_MMA) {
-        // ===== UMMA issuer =====
-        if (lane == 0 && mine > 0) {
+        // ===== UMMA issuer (the whole warp runs converged; one elected lane issues: see mma_bf16_ss_w) =====
+        if (mine > 0) {
             auto gemm1 = [&](int64_t k) {
                 const int s = int(k % XST), b = int(k & 1);
                 if (k >= 2) mbar_wait_site(&pre_empty[b], uint32_t((k >> 1) - 1) & 1u, 2);
                 mbar_wait_site(&st_full[k & 3], uint32_t(k >> 2) & 1u, 3);       // landed AND columns C, C+1 = (1/rstd, mean) written
                 tc_fence_after_sync();
                 issue_gemm1_tma(tmem, COL_PRE + uint32_t(b) * CP, smem_u32(sX + s * XSTAGE), smem_u32(sW1));
-                mma_commit(&pre_full[b]);
-                mma_commit(&x_empty[s]);
+                mma_commit_w(&pre_full[b]);
+                mma_commit_w(&x_empty[s]);
             };
             gemm1(0);
             for (int64_t k = 0; k < mine; ++k) {
@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
                 if (k >= NGI) mbar_wait_site(&gi_empty[g], uint32_t((k / NGI) - 1) & 1u, 4);
                 mbar_wait_site(u_full, uint32_t(k) & 1u, 5);
                 tc_fence_after_sync();
-                issue_row_gemm(tmem, COL_GI + uint32_t(g) * NC, smem_u32(sU), smem_u32(sWih), NC, NC, KCH / 2);
-                mma_commit(&gi_full[g]);
-                mma_commit(u_empty);
+                issue_row_gemm_w(tmem, COL_GI + uint32_t(g) * NC, smem_u32(sU), smem_u32(sWih), NC, NC, KCH / 2);
+                mma_commit_w(&gi_full[g]);
+                mma_commit_w(u_empty);
             }
         }
     } else if (warp < TF_W_EPU) {
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
         const int row = (warp - TF_W_STAT) * 32 + lane;
         for (int64_t k = 0; k < mine; ++k) {
             const int s = int(k % XST), q = int(k & 3);
-            mbar_wait_site(&x_full[s], uint32_t(k / XST) & 1u, 6);
+            mbar_wait_relaxed(&x_full[s], uint32_t(k / XST) & 1u, 6);
             const unsigned char* xs = sX + s * XSTAGE;
             float mean, rstd;
             row_stats(xs, row, C, mean, rstd);
@@ -285,9 +285,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
         const int c0 = 80 * half;
         for (int64_t k = 0; k < mine; ++k) {
             const int b = int(k & 1), q = int(k & 3);
-            mbar_wait_site(&st_full[q], uint32_t(k >> 2) & 1u, 7);
+            mbar_wait_relaxed(&st_full[q], uint32_t(k >> 2) & 1u, 7);
             const float2 st2 = sStat[q * TM + row];
-            mbar_wait_site(&pre_full[b], uint32_t(k >> 1) & 1u, 8);
+            mbar_wait_relaxed(&pre_full[b], uint32_t(k >> 1) & 1u, 8);
             tc_fence_after_sync();
             uint4 pk[10];
             unsigned long long mlo = 0ull, mhi = 0ull;             // sign bits of my columns [0,40) and [40,80)
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&pre_empty[b]);             // the accumulator set is free for GEMM1(k+2)
-            if (k > 0) mbar_wait_site(u_empty, uint32_t(k - 1) & 1u, 9);   // GEMM2(k-1) has read the u tile
+            if (k > 0) mbar_wait_relaxed(u_empty, uint32_t(k - 1) & 1u, 9);   // GEMM2(k-1) has read the u tile
 #pragma unroll
             for (int ch = 0; ch < 10; ++ch) *reinterpret_cast<uint4*>(sU + tile_off(TM, row, 10 * half + ch)) = pk[ch];
             {
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
             const int g = int(k % NGI);
             const int64_t item = int64_t(blockIdx.x) + k * G;
             unsigned char* gout = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(item) * NCH * TILE_CH;
-            mbar_wait_site(&gi_full[g], uint32_t(k / NGI) & 1u, 10);
+            mbar_wait_relaxed(&gi_full[g], uint32_t(k / NGI) & 1u, 10);
             tc_fence_after_sync();
 #pragma unroll 1
             for (int c16 = 0; c16 < NC / 16; ++c16) {
@@ -393,7 +393,7 @@ __device__ __forceinline__ void issue_wgrad_desc(uint32_t tmem_col, uint64_t ad,
     const uint32_t idesc = make_idesc_bf16(kTileRows, N, true, true);
 #pragma unroll
     for (int ks = 0; ks < int(kTileRows) / 16; ++ks) {
-        mma_bf16_ss(tmem_col, ad, bd, idesc, (acc || ks > 0) ? 1u : 0u);
+        mma_bf16_ss_w(tmem_col, ad, bd, idesc, (acc || ks > 0) ? 1u : 0u);
         ad += astep; bd += bstep;
     }
 }
@@ -455,27 +455,27 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
         if (IDX || lane == 0)
             produce_x<2, IDX>(a, &map128, &map64, sX, x_full, mine, G, [&](int64_t k) {
                 // stage k & 1 was last read by GEMM1 / Q of item k - 2; the dGI stage of item k - 1 is requested here too
-                mbar_wait_site(&q_done[k & 1], uint32_t((k >> 1) - 1) & 1u, 21);
+                mbar_wait_relaxed(&q_done[k & 1], uint32_t((k >> 1) - 1) & 1u, 21);
             });
     } else if (warp == TB_W_GPROD) {
         // ===== dGI producer (its own warp: it must not queue behind the x stage it does not depend on) =====
         if (lane == 0) {
             for (int64_t k = 0; k < mine; ++k) {
                 const int g = int(k & 1);
-                if (k >= 2) mbar_wait_site(&dw_done[g], uint32_t((k >> 1) - 1) & 1u, 22);
+                if (k >= 2) mbar_wait_relaxed(&dw_done[g], uint32_t((k >> 1) - 1) & 1u, 22);
                 const int64_t item = int64_t(blockIdx.x) + k * G;
                 mbar_expect_tx(&g_full[g], g_bytes);
                 bulk_g2s(sG + g * TB_G_BYTES, reinterpret_cast<const unsigned char*>(a.ws.gi) + size_t(item) * g_bytes, g_bytes, &g_full[g]);
             }
         }
     } else if (warp == TB_W_MMA) {
-        // ===== UMMA issuer =====
-        if (lane == 0 && mine > 0) {
+        // ===== UMMA issuer (whole warp converged, one elected lane issues) =====
+        if (mine > 0) {
             auto issue_du = [&](int64_t k) {
                 mbar_wait_site(&g_full[k & 1], uint32_t(k >> 1) & 1u, 23);
                 tc_fence_after_sync();
-                issue_row_gemm(tmem, COL_ACC, smem_u32(sG + (k & 1) * TB_G_BYTES), smem_u32(sWT), CP, CP, NC / 16);
-                mma_commit(du_full);
+                issue_row_gemm_w(tmem, COL_ACC, smem_u32(sG + (k & 1) * TB_G_BYTES), smem_u32(sWT), CP, CP, NC / 16);
+                mma_commit_w(du_full);
             };
             issue_du(0);
             const uint32_t ud = smem_u32(sUD);
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 TL(2);
                 tc_fence_after_sync();
                 issue_gemm1_tma(tmem, COL_ACC, xs, smem_u32(sW1));
-                mma_commit(pre_full);
+                mma_commit_w(pre_full);
                 const bool acc = k > 0;
                 const uint64_t a_dp = make_smem_desc(ud, 128, kTileChunk);                          // dpre' tile, M block o < 128
                 const uint64_t b_dp = make_smem_desc(ud + 16 * kTileChunk, 128, kTileChunk);        // dpre' tile, columns o >= 128 (N = 32)
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 issue_wgrad_desc(tmem + COL_QA + 128, a_dp, 256 >> 4, x32, 1024 >> 4, 32, acc);     // Q[o<128][i>=128]
                 issue_wgrad_desc(tmem + COL_QB0, x128, 2048 >> 4, b_dp, 256 >> 4, 32, acc);         // Q[o>=128][i<128]   (transposed: lane = i)
                 issue_wgrad_desc(tmem + COL_QB1, x32, 1024 >> 4, b_dp, 256 >> 4, 32, acc);          // Q[o>=128][i>=128]  (lanes 0..31)
-                mma_commit(&q_done[s]);
+                mma_commit_w(&q_done[s]);
                 TL(3);
                 mbar_wait_site(u_full, uint32_t(k) & 1u, 26);
                 TL(4);
@@ -510,10 +510,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 const uint64_t b_g = make_smem_desc(gs, 128, kTileChunk);
                 issue_wgrad_desc(tmem + COL_DW0, a_u0, 256 >> 4, b_g, 256 >> 4, uint32_t(NC), acc);  // dWih^T[c<128][g]
                 issue_wgrad_desc(tmem + COL_DW1, a_u1, 256 >> 4, b_g, 256 >> 4, uint32_t(NC), acc);  // dWih^T[c>=128][g]  (lanes 0..31; column C = bias)
-                mma_commit(&dw_done[s]);
+                mma_commit_w(&dw_done[s]);
                 TL(6);
             }
-            mma_commit(fin);
+            mma_commit_w(fin);
         }
     } else if (warp == TB_W_FIX) {
         // ===== LayerNorm columns of the landed x stage: x[:, C] = 1/rstd (-> db1), x[:, C+1] = mean (-> the fold correction) =====
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
             float2 st4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) st4[i] = a.ws.stats[size_t(item) * TM + 4 * lane + i];
-            mbar_wait_site(&x_full[s], uint32_t(k >> 1) & 1u, 27);
+            mbar_wait_relaxed(&x_full[s], uint32_t(k >> 1) & 1u, 27);
             unsigned char* xs = sX + s * XSTAGE;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
             uint4 pk[HALF_CH];
             {   // ---- dpre' = du * LeakyReLU'(pre) * rstd
                 TL(7);
-                mbar_wait_site(du_full, uint32_t(k) & 1u, 28);
+                mbar_wait_relaxed(du_full, uint32_t(k) & 1u, 28);
                 TL(8);
                 tc_fence_after_sync();
                 float v[40];
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                                         pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
                 tc_fence_before_sync();
                 TL(9);
-                if (k > 0) mbar_wait_site(&dw_done[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u, 29);      // dW(k-1) has read the u tile
+                if (k > 0) mbar_wait_relaxed(&dw_done[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u, 29);      // dW(k-1) has read the u tile
                 TL(10);
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sUD + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 TL(11);
             }
             {   // ---- u = LeakyReLU(rstd pre + fold)
-                mbar_wait_site(pre_full, uint32_t(k) & 1u, 30);
+                mbar_wait_relaxed(pre_full, uint32_t(k) & 1u, 30);
                 TL(12);
                 tc_fence_after_sync();
                 float v[40];
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 }
                 tc_fence_before_sync();
                 TL(13);
-                mbar_wait_site(&q_done[k & 1], uint32_t(k >> 1) & 1u, 31);                              // Q(k) has read the dpre' tile
+                mbar_wait_relaxed(&q_done[k & 1], uint32_t(k >> 1) & 1u, 31);                              // Q(k) has read the dpre' tile
                 TL(14);
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sUD + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
         }
         if (mine > 0) {
             // ---- flush the accumulators (raw sums: tc_post subtracts the fold column C+1)
-            mbar_wait_site(fin, 0, 32);
+            mbar_wait_relaxed(fin, 0, 32);
             tc_fence_after_sync();
             // QA: lane = o < 128, my 40 columns i
 #pragma unroll 1

@@ -61,6 +61,21 @@ __device__ __forceinline__ void mbar_wait_site(uint64_t* bar, uint32_t parity, i
     }
 }
 
+// Wait with back-off, for the many-warp roles.  Every failed try_wait is a shared-memory access; sixteen idle epilogue warps
+// polling flat out take a measurable share of the shared-memory port away from the UMMA operand reads (measured: the same
+// four UMMAs took 1060 cycles with the epilogue warps spinning, 320 alone).  The issuer / producer threads keep the tight loop.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int site) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    do {
+        __nanosleep(32);
+        if (++spins > (1u << 22)) {
+            printf("fvae: mbarrier wait timed out: site %d block %d thread %d parity %u\n", site, int(blockIdx.x), int(threadIdx.x), parity);
+            asm volatile("trap;");
+        }
+    } while (!mbar_try_wait(bar, parity));
+}
+
 // ---- bulk async copy (TMA, 1-D): global -> shared, completion counted in bytes on an mbarrier ----------------------
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -118,6 +133,26 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// Warp-converged issue: ALL 32 lanes of the issuer warp execute this with identical operands, one elected lane issues.  In a
+// `if (lane == 0)` region ptxas must assume divergent values and wraps every UMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// loop (~14 instructions, ~78 cycles per UMMA measured in situ -- more than a 128 x 32 x 16 UMMA takes to execute); converged,
+// the descriptors move to uniform registers with plain R2UR.
+__device__ __forceinline__ void mma_bf16_ss_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
 }
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -206,6 +241,19 @@ __device__ __forceinline__ void issue_wgrad_acc(uint32_t tmem, uint32_t dcol, ui
     for (int ks = 0; ks < int(kTileRows) / 16; ++ks) {
         mma_bf16_ss(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
         ad += 256 >> 4; bd += 256 >> 4;
+    }
+}
+
+// warp-converged forms of the two issue loops (see mma_bf16_ss_w)
+__device__ __forceinline__ void issue_row_gemm_w(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t b_addr, uint32_t brows,
+                                                 uint32_t N, int k16) {
+    const uint32_t idesc = make_idesc_bf16(kTileRows, N, false, false);
+    uint64_t ad = make_smem_desc(a_addr, kTileChunk, 128);
+    uint64_t bd = make_smem_desc(b_addr, brows * 16, 128);
+    const uint64_t astep = (2 * kTileChunk) >> 4, bstep = (2 * brows * 16) >> 4;
+    for (int ks = 0; ks < k16; ++ks) {
+        mma_bf16_ss_w(tmem + dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        ad += astep; bd += bstep;
     }
 }
 
