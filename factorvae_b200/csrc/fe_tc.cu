@@ -202,6 +202,7 @@ __global__ void tc_prep_kernel(PrepArgs a) {
 
 #include "fe_tc_front.cuh"   // ItemArgs, staging + LayerNorm, K1 front forward, K4 front backward
 #include "fe_tc_tma.cuh"     // warp-specialised TMA-fed front kernels (dense bf16 panels)
+#include "fe_tc_split.cuh"   // front backward as two roles in one launch
 
 // ---- K2: GRU forward -------------------------------------------------------------------------------------------
 struct GruArgs {
@@ -822,7 +823,17 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         if (!make_x_maps(&m128, &m64, x, d)) return FVAE_ERR_UNSUPPORTED;
         TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? 1 : 0, ws};
         cudaError_t ce2;
-        if (x.row_index) {
+        if (!getenv("FVAE_BACK_FUSED")) {
+            // two roles, one launch: even CTAs du -> dpre' -> Q^T, odd CTAs GEMM1 -> u -> dW_ih^T (fe_tc_split.cuh)
+            const int grid2 = (nsm & ~1) < 2 ? 2 : (nsm & ~1);
+            if (x.row_index) {
+                if ((ce2 = cudaFuncSetAttribute(tc_back_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TS_SMEM))) != cudaSuccess) return int(ce2);
+                tc_back_split_kernel<true><<<grid2, TS_THREADS, TS_SMEM, st>>>(m128, m64, ta); count_launch();
+            } else {
+                if ((ce2 = cudaFuncSetAttribute(tc_back_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TS_SMEM))) != cudaSuccess) return int(ce2);
+                tc_back_split_kernel<false><<<grid2, TS_THREADS, TS_SMEM, st>>>(m128, m64, ta); count_launch();
+            }
+        } else if (x.row_index) {
             if ((ce2 = cudaFuncSetAttribute(tc_back_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TB_SMEM))) != cudaSuccess) return int(ce2);
             tc_back_tma_kernel<true><<<grid, TB_THREADS, TB_SMEM, st>>>(m128, m64, ta); count_launch();
         } else {

@@ -59,11 +59,11 @@ __device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* m
 // while this item's copies fly).  `release(k)` blocks until stage k % XST may be overwritten.
 template <int XST, bool IDX, typename Release>
 __device__ __forceinline__ void produce_x(const TmaFrontArgs& a, const CUtensorMap* map128, const CUtensorMap* map64, unsigned char* sX,
-                                          uint64_t* x_full, int64_t mine, int64_t G, Release release) {
+                                          uint64_t* x_full, int64_t mine, int64_t first, int64_t G, Release release) {
     const int lane = threadIdx.x & 31;
     int4 nxt = make_int4(0, 0, 0, 0);
     auto fetch_idx = [&](int64_t k) {
-        const int64_t item = int64_t(blockIdx.x) + k * G;
+        const int64_t item = first + k * G;
         const int64_t st = item / a.T;
         const int t = int(item - st * a.T);
         int r[4];
@@ -81,7 +81,7 @@ __device__ __forceinline__ void produce_x(const TmaFrontArgs& a, const CUtensorM
         unsigned char* dst = sX + s * XSTAGE;
         if (!IDX) {
             if (lane == 0) {
-                const int64_t item = int64_t(blockIdx.x) + k * G;
+                const int64_t item = first + k * G;
                 const int64_t st = item / a.T;
                 const int t = int(item - st * a.T);
                 mbar_expect_tx(&x_full[s], XSTAGE);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
     if (warp == TF_W_PROD) {
         // ===== producer =====
         if (IDX || lane == 0)
-            produce_x<XST, IDX>(a, &map128, &map64, sX, x_full, mine, G,
+            produce_x<XST, IDX>(a, &map128, &map64, sX, x_full, mine, int64_t(blockIdx.x), G,
                                 [&](int64_t k) { mbar_wait_relaxed(&x_empty[k % XST], uint32_t((k / XST) - 1) & 1u, 1); });
     } else if (warp == TF_W_MMA) {
         // ===== UMMA issuer (the whole warp runs converged; one elected lane issues: see mma_bf16_ss_w) =====
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
     if (warp == TB_W_XPROD) {
         // ===== producer: x stages (TMA) =====
         if (IDX || lane == 0)
-            produce_x<2, IDX>(a, &map128, &map64, sX, x_full, mine, G, [&](int64_t k) {
+            produce_x<2, IDX>(a, &map128, &map64, sX, x_full, mine, int64_t(blockIdx.x), G, [&](int64_t k) {
                 // stage k & 1 was last read by GEMM1 / Q of item k - 2; the dGI stage of item k - 1 is requested here too
                 mbar_wait_relaxed(&q_done[k & 1], uint32_t((k >> 1) - 1) & 1u, 21);
             });
