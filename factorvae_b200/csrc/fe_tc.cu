@@ -734,9 +734,9 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
     const int64_t nitems = a.NT * d.T;
     const int grid = int(nitems < nsm ? nitems : nsm);
     if (tma_panel_ok(x, d)) {
-        CUtensorMap m128, m64;
-        if (make_x_maps(&m128, &m64, x, d)) {
-            TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? 1 : 0, ws};
+        XMaps xm;
+        if (make_x_maps(&xm, x, d)) {
+            TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? atoi(getenv("FVAE_TIMELINE")) : 0, ws};
             const size_t fixed = A_BYTES + W1_BYTES + size_t(KCH) * NC * 16 + 2 * CP * 4 + 4 * TM * 8 + 256 + 1024;
             const int xst = (fixed + 2 * XSTAGE <= kMaxSmem) ? 2 : 1;
             const int ngi = (320 + 2 * NC <= 512) ? 2 : 1;
@@ -745,7 +745,7 @@ int fe_tc_front_only(const FeDims& d, const fvae_panel& x, void* wsp, cudaStream
                 auto go = [&](auto kern) -> int {
                     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_t));
                     if (ce != cudaSuccess) return int(ce);
-                    kern<<<grid, TF_THREADS, smem_t, st>>>(m128, m64, ta); count_launch();
+                    kern<<<grid, TF_THREADS, smem_t, st>>>(xm, ta); count_launch();
                     return int(cudaGetLastError());
                 };
                 const bool idx = x.row_index != nullptr, xh = !tma_fused_backward_ok(x, d);
@@ -819,26 +819,26 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
     const int grid = int(nitems < nsm ? nitems : nsm);
     if (tma_fused_backward_ok(x, d)) {
         // one fused kernel: raw x rows (TMA) + dGI tiles (bulk copies) read once; GEMM1 recomputed; Q and dW_ih accumulated in TMEM
-        CUtensorMap m128, m64;
-        if (!make_x_maps(&m128, &m64, x, d)) return FVAE_ERR_UNSUPPORTED;
-        TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? 1 : 0, ws};
+        XMaps xm;
+        if (!make_x_maps(&xm, x, d)) return FVAE_ERR_UNSUPPORTED;
+        TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? atoi(getenv("FVAE_TIMELINE")) : 0, ws};
         cudaError_t ce2;
         if (!getenv("FVAE_BACK_FUSED")) {
             // two roles, one launch: even CTAs du -> dpre' -> Q^T, odd CTAs GEMM1 -> u -> dW_ih^T (fe_tc_split.cuh)
             const int grid2 = (nsm & ~1) < 2 ? 2 : (nsm & ~1);
             if (x.row_index) {
                 if ((ce2 = cudaFuncSetAttribute(tc_back_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TS_SMEM))) != cudaSuccess) return int(ce2);
-                tc_back_split_kernel<true><<<grid2, TS_THREADS, TS_SMEM, st>>>(m128, m64, ta); count_launch();
+                tc_back_split_kernel<true><<<grid2, TS_THREADS, TS_SMEM, st>>>(xm, ta); count_launch();
             } else {
                 if ((ce2 = cudaFuncSetAttribute(tc_back_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TS_SMEM))) != cudaSuccess) return int(ce2);
-                tc_back_split_kernel<false><<<grid2, TS_THREADS, TS_SMEM, st>>>(m128, m64, ta); count_launch();
+                tc_back_split_kernel<false><<<grid2, TS_THREADS, TS_SMEM, st>>>(xm, ta); count_launch();
             }
         } else if (x.row_index) {
             if ((ce2 = cudaFuncSetAttribute(tc_back_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TB_SMEM))) != cudaSuccess) return int(ce2);
-            tc_back_tma_kernel<true><<<grid, TB_THREADS, TB_SMEM, st>>>(m128, m64, ta); count_launch();
+            tc_back_tma_kernel<true><<<grid, TB_THREADS, TB_SMEM, st>>>(xm, ta); count_launch();
         } else {
             if ((ce2 = cudaFuncSetAttribute(tc_back_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TB_SMEM))) != cudaSuccess) return int(ce2);
-            tc_back_tma_kernel<false><<<grid, TB_THREADS, TB_SMEM, st>>>(m128, m64, ta); count_launch();
+            tc_back_tma_kernel<false><<<grid, TB_THREADS, TB_SMEM, st>>>(xm, ta); count_launch();
         }
         if ((ce2 = cudaGetLastError()) != cudaSuccess) return int(ce2);
         PostArgs pf{d.C, d.H, NC, w.ln_w, w.ln_b, w.W1, ws.q, ws.dwih, gr};

@@ -26,8 +26,7 @@ constexpr uint32_t TS_OFF_TAIL = TS_OFF_T + 2 * A_BYTES + 20480;       // max of
 constexpr size_t TS_SMEM = TS_OFF_TAIL + 256 + 1024;
 
 template <bool IDX>
-__global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __grid_constant__ CUtensorMap map128,
-                                                                      const __grid_constant__ CUtensorMap map64, TmaFrontArgs a) {
+__global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __grid_constant__ XMaps maps, TmaFrontArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
         }
         mbar_init(fin, 1);
         mbar_fence_init();
-        prefetch_tmap(&map128); prefetch_tmap(&map64);
+        prefetch_tmap(&maps.m128); prefetch_tmap(&maps.m64);
     }
     if (warp == TS_W_MMA) tmem_alloc<512>(tmem_slot);
     fence_async_smem();
@@ -75,10 +74,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
     const int64_t nitems = a.NT * a.T;
     const int64_t G = gridDim.x >> 1, first = blockIdx.x >> 1;          // the host launches an even grid
     const int64_t mine = nitems > first ? (nitems - 1 - first) / G + 1 : 0;
+    // diagnostics (FVAE_TIMELINE=1): CTAs 0 (role A) and 1 (role B) record clock64() at their hand-offs into ws.xh (unused by this path)
+    unsigned long long* tl = (a.timeline && blockIdx.x < 2 && lane == 0 && (warp == TS_W_MMA || warp == 0))
+                                 ? reinterpret_cast<unsigned long long*>(a.ws.xh) + size_t(blockIdx.x) * 4096 : nullptr;
+#define TLS(e) do { if (tl) tl[size_t(k) * 16 + (e)] = clock64(); } while (0)
 
     if (warp == TS_W_XPROD) {
         if (IDX || lane == 0)
-            produce_x<2, IDX>(a, &map128, &map64, sX, x_full, mine, first, G,
+            produce_x<2, IDX>(a, &maps, sX, x_full, mine, first, G,
                               [&](int64_t k) { mbar_wait_relaxed(&x_empty[k & 1], uint32_t((k >> 1) - 1) & 1u, 41); });
     } else if (warp == TS_W_GPROD) {
         if (lane == 0) {
@@ -126,10 +129,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
             for (int64_t k = 0; k < mine; ++k) {
                 const int s = int(k & 1);
                 const uint32_t xs = smem_u32(sX + s * XSTAGE), dp = smem_u32(sT + s * A_BYTES);
+                TLS(0);
                 mbar_wait_site(&t_full[s], uint32_t(k >> 1) & 1u, 45);           // dpre'(k) written, du(k) read out of TMEM
+                TLS(1);
                 tc_fence_after_sync();
                 if (k + 1 < mine) issue_du(k + 1);
+                TLS(2);
                 mbar_wait_site(&x_ready[s], uint32_t(k >> 1) & 1u, 46);
+                TLS(3);
                 tc_fence_after_sync();
                 const uint64_t b_dp = make_smem_desc(dp, 128, kTileChunk);                          // dpre' tile, MN-major, N = 160
                 const uint64_t x128 = make_smem_desc_sw(xs + XB0, 16384, 1024, 2);                  // x columns [0,128): M = 128
@@ -138,6 +145,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
                 issue_wgrad_desc(tmem + COL_Q2, x32, 1024 >> 4, b_dp, 256 >> 4, CP, k > 0);
                 mma_commit_w(&x_empty[s]);
                 mma_commit_w(&t_empty[s]);
+                TLS(4);
             }
             mma_commit_w(fin);
         } else if (mine > 0) {
@@ -155,10 +163,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
             gemm1(0);
             const uint32_t ud = smem_u32(sT);
             for (int64_t k = 0; k < mine; ++k) {
+                TLS(0);
                 if (k + 1 < mine) gemm1(k + 1);
+                TLS(1);
                 const int g = int(k & 1);
                 mbar_wait_site(&t_full[0], uint32_t(k) & 1u, 49);                 // u(k) written
+                TLS(2);
                 mbar_wait_site(&g_full[g], uint32_t(k >> 1) & 1u, 50);
+                TLS(3);
                 tc_fence_after_sync();
                 const uint64_t a_u0 = make_smem_desc(ud, 128, kTileChunk), a_u1 = make_smem_desc(ud + 16 * kTileChunk, 128, kTileChunk);
                 const uint64_t b_g = make_smem_desc(smem_u32(sG + g * TS_G_BYTES), 128, kTileChunk);
@@ -166,6 +178,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
                 issue_wgrad_desc(tmem + COL_DW1, a_u1, 256 >> 4, b_g, 256 >> 4, uint32_t(NC), k > 0);   // dWih^T[c>=128][g] (lanes 0..31; column C = bias)
                 mma_commit_w(&t_empty[0]);
                 mma_commit_w(&g_empty[g]);
+                TLS(4);
             }
             mma_commit_w(fin);
         }
@@ -201,7 +214,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
                     nm = a.ws.mask[size_t(nitem) * 4 * TM + part * TM + row];
                     nr = a.ws.stats[size_t(nitem) * TM + row].y;
                 }
+                TLS(8);
                 mbar_wait_relaxed(&acc_full[0], uint32_t(k) & 1u, 51);
+                TLS(9);
                 tc_fence_after_sync();
                 float v[40];
                 ld40(0, v);
@@ -216,13 +231,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
                                         pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
                 tc_fence_before_sync();
                 const int s = int(k & 1);
+                TLS(10);
                 if (k >= 2) mbar_wait_relaxed(&t_empty[s], uint32_t((k >> 1) - 1) & 1u, 52);          // Q(k-2) has read this dpre' tile
+                TLS(11);
                 unsigned char* dst = sT + s * A_BYTES;
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(dst + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_full[s]);
+                TLS(12);
                 mbits = nm; rstd = nr;
             }
         } else {
@@ -233,7 +251,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
                 float nr = 1.f;
                 if (k + 1 < mine) nr = a.ws.stats[size_t(first + (k + 1) * G) * TM + row].y;
                 const int b = int(k & 1);
+                TLS(8);
                 mbar_wait_relaxed(&acc_full[b], uint32_t(k >> 1) & 1u, 53);
+                TLS(9);
                 tc_fence_after_sync();
                 float v[40];
                 ld40(uint32_t(b) * CP, v);
@@ -257,12 +277,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[b]);
+                TLS(10);
                 if (k > 0) mbar_wait_relaxed(&t_empty[0], uint32_t(k - 1) & 1u, 54);                  // dW(k-1) has read the u tile
+                TLS(11);
 #pragma unroll
                 for (int ch = 0; ch < HALF_CH; ++ch) *reinterpret_cast<uint4*>(sT + tile_off(TM, row, HALF_CH * part + ch)) = pk[ch];
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_full[0]);
+                TLS(12);
                 rstd = nr;
             }
         }
@@ -302,4 +325,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_back_split_kernel(const __gr
     tc_fence_before_sync();
     __syncthreads();
     if (warp == TS_W_MMA) tmem_dealloc<512>(tmem);
+#undef TLS
+    if (a.timeline && int(blockIdx.x) == a.timeline - 1 && tid == 0) {     // FVAE_TIMELINE=1: role A (CTA 0), =2: role B (CTA 1)
+        __threadfence();
+        const unsigned long long* t = reinterpret_cast<const unsigned long long*>(a.ws.xh) + size_t(blockIdx.x) * 4096;
+        printf(roleA ? "fvae split timeline role A (cycles from loop top): MMA: t_full du_next x_ready Q_issued | EPI: wait acc_full computed t_empty_seen arrived\n"
+                     : "fvae split timeline role B (cycles from loop top): MMA: gemm1_next t_full g_full dW_issued | EPI: wait acc_full computed t_empty_seen arrived\n");
+        for (int64_t k = 2; k < (mine < 14 ? mine : 14); ++k) {
+            const unsigned long long t0 = t[k * 16];
+            printf("%c item %2d:", roleA ? 'A' : 'B', int(k));
+            for (int e = 1; e < 5; ++e) printf(" %6lld", (long long)(t[k * 16 + e] - t0));
+            printf("  |");
+            for (int e = 8; e < 13; ++e) printf(" %6lld", (long long)(t[k * 16 + e] - t0));
+            printf("  | next +%lld\n", (long long)(t[(k + 1) * 16] - t0));
+        }
+    }
 }
