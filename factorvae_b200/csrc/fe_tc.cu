@@ -823,7 +823,7 @@ int fe_tc_backward(const FeDims& d, const fvae_panel& x, const FeW& w, const FeG
         if (!make_x_maps(&xm, x, d)) return FVAE_ERR_UNSUPPORTED;
         TmaFrontArgs ta{d.T, d.C, NC, a.NT, d.S, x.row_index, int32_t(x.num_rows), getenv("FVAE_TIMELINE") ? atoi(getenv("FVAE_TIMELINE")) : 0, ws};
         cudaError_t ce2;
-        if (!getenv("FVAE_BACK_FUSED")) {
+        if (getenv("FVAE_BACK_SPLIT")) {
             // two roles, one launch: even CTAs du -> dpre' -> Q^T, odd CTAs GEMM1 -> u -> dW_ih^T (fe_tc_split.cuh)
             const int grid2 = (nsm & ~1) < 2 ? 2 : (nsm & ~1);
             if (x.row_index) {
