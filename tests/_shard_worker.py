@@ -67,7 +67,7 @@ def main():
     same_everywhere = bool((lo_ == hi_).item())
     ok = True
     if rank == 0:
-        solo = DateShardedStep(L, flat, precision=precision, group=None, seed=11)
+        solo = DateShardedStep(L, flat, precision=precision, group=None, seed=11, collective="nccl")   # no collective at construction
         solo.world = 1                                   # the whole batch on this GPU, no collective
         pall = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=dev)
         o1, _ = solo.step(torch.cat(xs), torch.cat(ys), pall, global_dates=B, unit_base=0, train=True)
