@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-B200 comparator")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"], help="gradient exchange: the one-kernel NVLink all-reduce or ncclAllReduce")
     ap.add_argument("--windows-e2e", action="store_true", help="also time the legacy variant that ships every window over PCIe")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -324,7 +325,7 @@ def main():
         gen.manual_seed(1234 + d0 + d)
         x[d * N:(d + 1) * N] = torch.randn(N, T, C_FEATURES, generator=gen, device=dev).clamp_(-3, 3).to(pdt)
         y[d * N:(d + 1) * N] = torch.randn(N, generator=gen, device=dev)
-    stepper = DateShardedStep(layout, flat, precision=precision, seed=42)
+    stepper = DateShardedStep(layout, flat, precision=precision, seed=42, collective=args.collective)
     unit_base = d0 * N
     lib = _cabi.lib()
     micro = min(wl["micro"], B)
@@ -567,7 +568,9 @@ def main():
                            "panel_layout": "x[S][T][%d] %s, %d features per row used (row pitch padded to 16 bytes)" % (x_store.shape[2], args.panel, C_FEATURES),
                            "noise": "in-kernel Philox (eps + dropout masks), keyed by global unit id",
                            "parallelism": f"dp{world} over dates", "dates_per_gpu": B, "micro_batch_dates": micro,
-                           "collective": "one all-reduce of the flat fp32 gradient (+ loss) per step" if world > 1 else "none"},
+                           "collective": ("one all-reduce of the flat fp32 gradient (+ loss) per step: " +
+                                          ("one kernel over NVLink peer memory (fvae_p2p_allreduce)" if stepper.p2p is not None else "ncclAllReduce"))
+                                         if world > 1 else "none"},
                 "loss": loss_val, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "e2e": e2e}
         print(json.dumps(line), flush=True)
