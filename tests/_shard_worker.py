@@ -81,7 +81,9 @@ def main():
         print(f"G={world} {precision}: grad rel-L2 {rel:.3e} max-rel {mx:.3e}; loss {loss_all:.7f} vs {l1:.7f} (rel {lrel:.2e}); "
               f"per-unit outputs bit-identical: {same}; p2p vs nccl rel-L2 {d_coll:.2e}; p2p result identical on all ranks: "
               f"{same_everywhere}; p2p active: {st.p2p is not None}", flush=True)
-        ok = rel <= 2e-6 and mx <= 2e-5 and lrel <= 1e-6 and same and d_coll <= 2e-6 and same_everywhere and st.p2p is not None
+        # fp32 round-off: the weight-gradient sums are float atomics (order free), bf16 mode adds the tensor-core heads' own
+        tol = 2e-6 if precision == "fp32" else 1e-5
+        ok = rel <= tol and mx <= 2e-5 and lrel <= 1e-6 and same and d_coll <= tol and same_everywhere and st.p2p is not None
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -54,7 +54,7 @@ def test_sharded_gradient_equals_single_gpu_gradient_emulated(precision, G, cuda
             assert torch.allclose(o["mu_prior"], o1["mu_prior"][d0:d1], rtol=1e-5, atol=1e-6)
     gG, lG = total[: L.total], float(total[L.total])
     assert abs(lG - l1) <= 1e-6 * abs(l1), (lG, l1)
-    assert float((gG - g1).norm() / g1.norm()) <= 2e-6
+    assert float((gG - g1).norm() / g1.norm()) <= (2e-6 if precision == "fp32" else 1e-5)
     assert float((gG - g1).abs().max() / g1.abs().max()) <= 2e-5
 
 
