@@ -310,15 +310,15 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
             mbar_wait_relaxed(&pre_full[b], uint32_t(k >> 1) & 1u, 8);
             tc_fence_after_sync();
             uint4 pk[10];
-            unsigned long long mlo = 0ull, mhi = 0ull;             // sign bits of my columns [0,40) and [40,80)
+            uint32_t mw[3] = {0u, 0u, 0u};                         // sign bits of my 80 columns, 32 per word (one predicated OR-immediate each)
 #pragma unroll
             for (int gq = 0; gq < 5; ++gq) {
                 float v[16];
                 tmem_ld16(tmem_addr(tmem, lane_base, COL_PRE + uint32_t(b) * CP + c0 + gq * 16), v);
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const int cc = gq * 16 + e;
-                    if (v[e] > 0.f) { if (cc < 40) mlo |= 1ull << cc; else mhi |= 1ull << (cc - 40); }
+                    const int cc = gq * 16 + e;                    // compile-time after unrolling
+                    if (v[e] > 0.f) mw[cc >> 5] |= 1u << (cc & 31);
                 }
                 uint32_t w[8];
 #pragma unroll
@@ -350,8 +350,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
                     for (int ch = 0; ch < 10; ++ch) *reinterpret_cast<uint4*>(gu + tile_off(TM, row, 10 * half + ch)) = pk[ch];
                 }
                 unsigned long long* gm = a.ws.mask + size_t(item) * 4 * TM;
-                gm[(2 * half) * TM + row] = mlo;
-                gm[(2 * half + 1) * TM + row] = mhi;
+                // saved format: 40 bits per (row, part of 40 columns)
+                gm[(2 * half) * TM + row] = (unsigned long long)mw[0] | ((unsigned long long)(mw[1] & 0xFFu) << 32);
+                gm[(2 * half + 1) * TM + row] = (unsigned long long)(mw[1] >> 8) | ((unsigned long long)mw[2] << 24);
             }
             fence_async_smem();
             __syncwarp();
