@@ -11,7 +11,7 @@ Workloads (BASELINE.json configs; H = K, M = 128):
   cfg2  256 dates x 300, T=20, K=20   (DEFAULT, N=1..8)    per GPU, weak scaling: every rank processes 256 dates
   cfg3  256 dates x 500, T=60, K=60                        per GPU, weak scaling
   cfg4  512 dates x 1000, T=20, K=48  GLOBAL batch         strong scaling: 512 / N dates per GPU, micro-batches of 64 dates
-  cfg5  1024 dates x 3000, T=60, K=60 GLOBAL batch         strong scaling: 1024 / N dates per GPU, micro-batches of 32 dates
+  cfg5  1024 dates x 3000, T=60, K=60 GLOBAL batch         strong scaling: 1024 / N dates per GPU, micro-batches of 128 dates
 `--gpus N` without `--workload` runs cfg2 (the configuration BASELINE.json's metric is quoted on for one GPU).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job units/s with the panel resident in HBM; `e2e` = the same through the
@@ -40,7 +40,8 @@ WORKLOADS = {
     "cfg3": dict(B=256, N=500, T=60, H=60, K=60, M=128, scaling="weak", micro=256),
     # global batches split over the ranks (strong scaling), processed in micro-batches of `micro` dates
     "cfg4": dict(B=512, N=1000, T=20, H=48, K=48, M=128, scaling="strong", micro=64),
-    "cfg5": dict(B=1024, N=3000, T=60, H=60, K=60, M=128, scaling="strong", micro=32),
+    # micro = 128: the fp32 CUDA-core heads (H, K > 32) run one CTA per date -- 32-date micro-batches left 116 of 148 SMs idle there
+    "cfg5": dict(B=1024, N=3000, T=60, H=60, K=60, M=128, scaling="strong", micro=128),
 }
 C_FEATURES = 158
 METRIC = "dates x stocks / sec per ELBO step (fwd+bwd), K=20 C=158"

@@ -53,6 +53,7 @@ class DateShardedStep:
         # gradient buffer with a 4-float tail: [total] = loss (written by the kernels), rest padding
         self.gradbuf = torch.zeros(layout.total + 4, dtype=torch.float32, device=flat.device)
         self.workspace: Optional[torch.Tensor] = None
+        self._outs: Dict = {}           # output tensors of the step, allocated once per batch shape and reused
         self.step_index = 0
         self._dev: Dict[str, torch.Tensor] = {}
 
@@ -69,7 +70,7 @@ class DateShardedStep:
         tail); no collective."""
         noise = dict(eps=eps, keep_mask=keep_mask) if eps is not None else dict(philox=(self.seed, self.step_index, unit_base))
         out, st = engine.elbo_forward(self.layout, self.flat, x, y, date_ptr, train=train, precision=self.precision,
-                                      workspace=self.workspace, loss_out=self.loss, **noise)
+                                      workspace=self.workspace, loss_out=self.loss, out_cache=self._outs, **noise)
         self.workspace = st.workspace
         engine.elbo_backward(self.layout, st, grad=self.grad)
         return out, st
