@@ -459,8 +459,14 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
     extern __shared__ __align__(16) float smem_raw[];
     const int H = a.H, K = a.K, M = a.M;
     const int d = blockIdx.x, tid = threadIdx.x;
+    // blockIdx.y = slice of the date's stock chunks (the sweep over stocks needs only the per-date vectors: every slice
+    // recomputes them, slice 0 alone adds the per-date parameter gradients).  One CTA per date left 84 of 148 SMs idle at
+    // 64 dates per GPU (cfg4) -- the sweep was 52 % of that step.
+    const int slice_y = blockIdx.y, nslice_y = gridDim.y;
+    const bool lead = slice_y == 0;
     const int p0 = a.date_ptr[d], n = a.date_ptr[d + 1] - p0;
     if (n <= 0) return;
+    if (slice_y * CH >= n) return;                          // nothing to sweep for this slice
     const int NF = M + 2 * K + H;
     const int ZLD = NF | 1;
     // shared memory
@@ -549,11 +555,12 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         const float dsg2 = a.sv.clamp_prior[size_t(d) * K + k] ? 0.f : g_s2;
         const float dpre2 = dsg2 * softplus_grad(a.sv.pre_sg_prior[size_t(d) * K + k]);
         dmupost[k] = dmu1; dprepost[k] = dpre1; dmuprior[k] = -g_m1; dpreprior[k] = dpre2;
-        atomicAdd(g.bmu + k, dmu1);
-        atomicAdd(g.bsig + k, dpre1);
+        if (lead) { atomicAdd(g.bmu + k, dmu1); atomicAdd(g.bsig + k, dpre1); }
     }
     __syncthreads();
-    if ((M & 3) == 0) {                                     // dWmu, dWsig: one vector reduction per 4 portfolios
+    if (!lead) {
+        // per-date parameter gradients belong to slice 0
+    } else if ((M & 3) == 0) {                              // dWmu, dWsig: one vector reduction per 4 portfolios
         for (int i4 = tid; i4 < K * M / 4; i4 += NT) {
             const int idx = 4 * i4, k = idx / M, j = idx % M;
             const float a1 = dmupost[k], a2 = dprepost[k];
@@ -581,7 +588,7 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         for (int k = tid; k < K; k += NT) { sbm += dmuprior[k]; sbs += dpreprior[k]; }
         sbm = block_sum(sbm, red);
         sbs = block_sum(sbs, red);
-        if (tid == 0) { atomicAdd(g.bpm, sbm); atomicAdd(g.bps, sbs); }
+        if (tid == 0 && lead) { atomicAdd(g.bpm, sbm); atomicAdd(g.bps, sbs); }
     }
     for (int j = tid; j < H; j += NT) {
         float a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -595,10 +602,10 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
             tmpKH[k * H + j] = dpre;                         // d hm_pre
             a3 += dpre;
         }
-        atomicAdd(g.wpm + j, a1); atomicAdd(g.wps + j, a2); atomicAdd(g.bl + j, a3);
+        if (lead) { atomicAdd(g.wpm + j, a1); atomicAdd(g.wps + j, a2); atomicAdd(g.bl + j, a3); }
     }
     __syncthreads();
-    for (int idx = tid; idx < H * H; idx += NT) {          // dWl[j][h] = sum_k dhm_pre[k][j] ctx[k][h]
+    for (int idx = tid; lead && idx < H * H; idx += NT) {  // dWl[j][h] = sum_k dhm_pre[k][j] ctx[k][h]
         const int j = idx / H, h = idx % H;
         float v = 0.f;
         for (int k = 0; k < K; ++k) v = fmaf(tmpKH[k * H + j], a.sv.ctx[(size_t(d) * K + k) * H + h], v);
@@ -619,13 +626,14 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         const int k = idx / H, h = idx % H;
         float v = 0.f;
         if (!bad[k]) {
-            atomicAdd(g.bv + idx, tmpKH[idx]);
+            if (lead) atomicAdd(g.bv + idx, tmpKH[idx]);
             const float* wv = a.w.Wv + size_t(k) * H * H;
             for (int j = 0; j < H; ++j) v = fmaf(wv[j * H + h], tmpKH[k * H + j], v);
         }
         dps[idx] = v;
     }
-    if ((H & 3) == 0) {                                     // dWv[k][j][h] = dctx[k][j] pooled[k][h], 4 h per reduction
+    if (!lead) {
+    } else if ((H & 3) == 0) {                              // dWv[k][j][h] = dctx[k][j] pooled[k][h], 4 h per reduction
         for (int i4 = tid; i4 < K * H * H / 4; i4 += NT) {
             const int idx = 4 * i4, k = idx / (H * H), r = idx % (H * H), j = r / H, h = r % H;
             if (!bad[k]) {
@@ -682,7 +690,7 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
 #pragma unroll
         for (int h = 0; h < HP; ++h) acc[b][h] = 0.f;
     }
-    for (int i0 = 0; i0 < n; i0 += CH) {
+    for (int i0 = slice_y * CH; i0 < n; i0 += nslice_y * CH) {
         const int cn = min(CH, n - i0);
         __syncthreads();
         stage_chunk<HP>(a, Smem{Es}, p0, i0, cn);
@@ -956,10 +964,20 @@ int heads_backward(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t 
     const bool wsm = HP <= 32 && bwd_smem_bytes(HP, a.H, a.K, a.M, true) <= 110 * 1024;   // keep two CTAs per SM
     const size_t smem = bwd_smem_bytes(HP, a.H, a.K, a.M, wsm);
     int rc;
+    // slices of a date's stocks over blockIdx.y: enough CTAs for two per SM, never more slices than 64-stock chunks
+    int nsm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    int split = (2 * nsm + a.B - 1) / a.B;
+    const int max_chunks = (int((int64_t(a.S) + a.B - 1) / a.B) + CH - 1) / CH;      // of an average date
+    if (split > max_chunks) split = max_chunks;
+    if (split > 16) split = 16;
+    if (split < 1) split = 1;
+    const dim3 grid_b(a.B, split);
 #define FVAE_LAUNCH_BWD(HPV, NBV, WSMV)                                                      \
     do {                                                                                     \
         if ((rc = set_smem(heads_bwd_kernel<HPV, NBV, WSMV>, smem)) != 0) return rc;         \
-        heads_bwd_kernel<HPV, NBV, WSMV><<<a.B, NT, smem, stream>>>(a, g, dE); count_launch(); \
+        heads_bwd_kernel<HPV, NBV, WSMV><<<grid_b, NT, smem, stream>>>(a, g, dE); count_launch(); \
     } while (0)
     if (HP == 20) {
         if (wsm) { if (NB == 1) FVAE_LAUNCH_BWD(20, 1, true); else FVAE_LAUNCH_BWD(20, 2, true); }
