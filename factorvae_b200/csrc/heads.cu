@@ -968,16 +968,22 @@ int heads_backward(const HeadsArgs& a, const HeadsG& g, float* dE, cudaStream_t 
     int nsm = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    int split = (2 * nsm + a.B - 1) / a.B;
-    const int max_chunks = (int((int64_t(a.S) + a.B - 1) / a.B) + CH - 1) / CH;      // of an average date
-    if (split > max_chunks) split = max_chunks;
-    if (split > 16) split = 16;
-    if (split < 1) split = 1;
-    const dim3 grid_b(a.B, split);
+    // one wave: as many slices per date as resident CTAs allow (occupancy of the chosen instantiation, queried below)
+    int split = 1;
+    const int max_chunks = (int((int64_t(a.S) + a.B - 1) / a.B) + CH - 1) / CH;      // 64-stock chunks of an average date
+    auto pick_split = [&](int occ) {
+        int sp = (nsm * (occ < 1 ? 1 : occ)) / a.B;
+        if (sp > max_chunks) sp = max_chunks;
+        if (sp > 16) sp = 16;
+        return sp < 1 ? 1 : sp;
+    };
 #define FVAE_LAUNCH_BWD(HPV, NBV, WSMV)                                                      \
     do {                                                                                     \
         if ((rc = set_smem(heads_bwd_kernel<HPV, NBV, WSMV>, smem)) != 0) return rc;         \
-        heads_bwd_kernel<HPV, NBV, WSMV><<<grid_b, NT, smem, stream>>>(a, g, dE); count_launch(); \
+        int occ = 1;                                                                         \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, heads_bwd_kernel<HPV, NBV, WSMV>, NT, smem); \
+        split = pick_split(occ);                                                             \
+        heads_bwd_kernel<HPV, NBV, WSMV><<<dim3(a.B, split), NT, smem, stream>>>(a, g, dE); count_launch(); \
     } while (0)
     if (HP == 20) {
         if (wsm) { if (NB == 1) FVAE_LAUNCH_BWD(20, 1, true); else FVAE_LAUNCH_BWD(20, 2, true); }
