@@ -13,7 +13,7 @@ F32, BF16 = 0, 1
 PREC_FP32, PREC_BF16_TC = 0, 1
 FLAG_TRAIN, FLAG_PHILOX = 1, 2
 FILL_NONE, FILL_FFILL, FILL_FFILL_BFILL = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 SECTIONS = [
     "LN_W", "LN_B", "W1", "B1", "WIH", "WHH", "BIH", "BHH",
@@ -43,6 +43,10 @@ class Noise(C.Structure):
 class Outputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("loss", "date_loss", "yhat", "mu_y", "sigma_y", "mu_post", "sigma_post",
                                           "mu_prior", "sigma_prior")]
+
+
+class Parts(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("z_mu", "z_sigma", "alpha_mu", "alpha_sigma", "beta", "context")]
 
 
 _lib = None
@@ -82,6 +86,9 @@ def lib() -> C.CDLL:
     L.fvae_fe_forward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i32, vp, vp, i64, vp]
     L.fvae_fe_backward.restype = C.c_int
     L.fvae_fe_backward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i32, vp, vp, vp, i64, vp]
+    L.fvae_heads_parts.restype = C.c_int
+    L.fvae_heads_parts.argtypes = [C.POINTER(Shape), vp, vp, vp, vp, C.POINTER(Noise), u32, C.POINTER(Parts), C.POINTER(Outputs),
+                                   vp, i64, vp]
     L.fvae_debug_front_forward.restype = C.c_int
     L.fvae_debug_front_forward.argtypes = [C.POINTER(Shape), C.POINTER(Panel), vp, i64, vp]
     L.fvae_debug_noise.restype = C.c_int
@@ -115,7 +122,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ["fvae_abi_version", "fvae_debug_launch_count", "fvae_debug_front_forward", "fvae_debug_noise", "fvae_status_string", "fvae_param_offsets", "fvae_param_count", "fvae_workspace_bytes",
-           "fvae_elbo_forward", "fvae_elbo_backward", "fvae_predict", "fvae_fe_forward", "fvae_fe_backward",
+           "fvae_elbo_forward", "fvae_elbo_backward", "fvae_predict", "fvae_fe_forward", "fvae_fe_backward", "fvae_heads_parts",
            "fvae_workspace_latent", "fvae_window_index", "fvae_gather_windows", "fvae_adam_step", "fvae_rank_ic",
            "fvae_p2p_buffer_bytes", "fvae_p2p_alloc", "fvae_p2p_open", "fvae_p2p_close", "fvae_p2p_free", "fvae_p2p_allreduce"]
 

@@ -156,9 +156,6 @@ __device__ __forceinline__ void issue_gemm1_tma(uint32_t tmem, uint32_t dcol, ui
     }
 }
 
-__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(n) : "memory");
-}
 
 // row statistics of one staged row (thread = row): sums over exactly C = 158 features
 __device__ __forceinline__ void row_stats(const unsigned char* xs, int row, int C, float& mean, float& rstd) {
@@ -195,9 +192,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
     unsigned char* sU = sX + XST * XSTAGE;                     // u tile [20][128][16]
     unsigned char* sW1 = sU + A_BYTES;                         // W1n image [20][160][16]
     unsigned char* sWih = sW1 + W1_BYTES;                      // W_ih image [20][NC][16]  (bias in column C)
-    float* sB1 = reinterpret_cast<float*>(sWih + uint32_t(KCH) * NC * 16);   // b1f[160]
-    float* sW1s = sB1 + CP;                                    // w1s[160]
-    float2* sStat = reinterpret_cast<float2*>(sW1s + CP);      // [4][128] (-mean rstd, rstd)
+    float2* sStat = reinterpret_cast<float2*>(sWih + uint32_t(KCH) * NC * 16 + 2 * CP * 4);      // [4][128] (-mean rstd, rstd)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 4 * TM);
     uint64_t* x_full = bars;            // [2]
     uint64_t* x_empty = bars + 2;       // [2]  GEMM1 commit + 4 stats warps
@@ -212,7 +207,6 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
 
     copy_image(sW1, a.ws.w1n, W1_BYTES);
     copy_image(sWih, a.ws.wih, uint32_t(KCH) * NC * 16);
-    for (int i = tid; i < CP; i += TF_THREADS) { sB1[i] = a.ws.b1f[i]; sW1s[i] = a.ws.w1s[i]; }
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 5); mbar_init(&pre_full[i], 1); mbar_init(&pre_empty[i], 8);
                                       mbar_init(&gi_full[i], 1); mbar_init(&gi_empty[i], 4); }
@@ -434,9 +428,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
     unsigned char* sUD = smem + TB_OFF_UD;
     unsigned char* sW1 = smem + TB_OFF_W1;
     unsigned char* sWT = smem + TB_OFF_WT;
-    float* sB1 = reinterpret_cast<float*>(smem + TB_OFF_TAIL);
-    float* sW1s = sB1 + CP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW1s + CP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_OFF_TAIL);
     uint64_t* x_full = bars;            // [2] tx
     uint64_t* x_ready = bars + 2;       // [2] fix-up warp
     uint64_t* q_done = bars + 4;        // [2] commit: GEMM1(k) + Q(k) complete -> x stage and the dpre' tile are free
@@ -451,7 +443,6 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
 
     copy_image(sW1, a.ws.w1n, W1_BYTES);
     copy_image(sWT, a.ws.wihT, uint32_t(NC / 8) * CP * 16);
-    for (int i = tid; i < CP; i += TB_THREADS) { sB1[i] = a.ws.b1f[i]; sW1s[i] = a.ws.w1s[i]; }
     for (uint32_t i = tid; i < (2 * TB_G_BYTES + A_BYTES) / 16; i += TB_THREADS) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_ready[i], 1); mbar_init(&q_done[i], 1); mbar_init(&g_full[i], 1); mbar_init(&dw_done[i], 1); }

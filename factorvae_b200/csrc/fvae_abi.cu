@@ -157,6 +157,7 @@ HeadsArgs make_heads_args(const fvae_shape& s, const Workspace& W, const float* 
     a.S = s.S; a.B = s.B; a.H = s.H; a.K = s.K; a.M = s.M;
     a.date_ptr = date_ptr; a.e = W.e; a.y = y; a.noise = nz; a.flags = flags; a.predict = predict;
     a.out = out; a.w = hw; a.sv = W.sv; a.use_tc = 0;
+    a.parts = HeadsParts{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     return a;
 }
 
@@ -304,6 +305,33 @@ int fvae_fe_backward(const fvae_shape* shape, const fvae_panel* x, const float* 
     bind_grads(grad, L, fg, hg);
     const FeDims fd{shape->S, shape->T, shape->C, shape->H};
     return fe_backward_any(fd, *x, fw, fg, precision, de, W.fe_ws, static_cast<cudaStream_t>(stream));
+}
+
+int fvae_heads_parts(const fvae_shape* shape, const float* latent, const float* y, const int32_t* date_ptr, const float* params,
+                     const fvae_noise* noise, uint32_t flags, const fvae_parts* parts, const fvae_outputs* out, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    int rc;
+    const int predict = y ? 0 : 1;
+    if ((rc = check_shape(shape, FVAE_PREC_FP32)) != 0) return rc;
+    if ((rc = check_noise(noise, flags)) != 0) return rc;
+    if ((rc = check_outputs(out, predict != 0)) != 0) return rc;
+    if (!latent || !date_ptr || !params || !workspace) return FVAE_ERR_NULL;
+    if (parts && ((parts->z_mu == nullptr) != (parts->z_sigma == nullptr) || (parts->alpha_mu == nullptr) != (parts->alpha_sigma == nullptr)))
+        return FVAE_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return FVAE_ERR_WORKSPACE;
+    Workspace W = carve(*shape, FVAE_PREC_FP32, workspace);
+    if (W.bytes > workspace_bytes) return FVAE_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Layout L = make_layout(shape->C, shape->H, shape->K, shape->M);
+    FeW fw; HeadsW hw;
+    bind_params(params, L, fw, hw);
+    HeadsArgs a = make_heads_args(*shape, W, y, date_ptr, *noise, flags, predict, *out, hw);
+    a.e = latent;                                     // the caller's stock latents, read in place
+    if (parts) a.parts = HeadsParts{parts->z_mu, parts->z_sigma, parts->alpha_mu, parts->alpha_sigma, parts->beta, parts->context};
+    if ((rc = heads_prep(a, false, st)) != 0) return rc;
+    if ((rc = heads_forward(a, st)) != 0) return rc;
+    if (!predict && (rc = loss_reduce(out->date_loss, shape->B, out->loss, st)) != 0) return rc;
+    return FVAE_OK;
 }
 
 int fvae_debug_front_forward(const fvae_shape* shape, const fvae_panel* x, void* workspace, int64_t workspace_bytes, void* stream) {

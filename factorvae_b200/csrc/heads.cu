@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
         }
         s.ctx[idx] = v;
         a.sv.ctx[size_t(d) * K * H + idx] = v;
+        if (a.parts.context) a.parts.context[size_t(d) * K * H + idx] = v;
     }
     __syncthreads();
     float* hm = s.F;     // [K][H] scratch (F is not live yet)
@@ -338,6 +339,11 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
         a.sv.pre_sg_prior[size_t(d) * K + k] = pre;
         a.sv.clamp_prior[size_t(d) * K + k] = cl;
         if (a.predict) { s.muz[k] = mu; s.sgz[k] = sg; }
+        if (a.parts.z_mu) {                                    // FactorDecoder.forward on its own: the caller's factors, :117 clamp
+            const float zs = a.parts.z_sigma[size_t(d) * K + k];
+            s.muz[k] = a.parts.z_mu[size_t(d) * K + k];
+            s.sgz[k] = (zs == 0.f) ? kSigmaFloor : zs;
+        }
     }
     __syncthreads();
 
@@ -394,6 +400,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
             }
             if (i < cn && part == 0) {
                 const float asig = softplus(asp + a.w.bas[0]);
+                if (a.parts.alpha_mu) { a.parts.alpha_mu[p0 + i0 + i] = amu + a.w.bam[0]; a.parts.alpha_sigma[p0 + i0 + i] = asig; }
                 mu += amu + a.w.bam[0];
                 const float sy = sqrtf(var + asig * asig + 1e-6f);
                 const float yh = fmaf(s.aux0[i], sy, mu);
@@ -407,6 +414,10 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
             } else if (i < CH && part == 0) {
                 s.aux1[i] = 0.f; s.ys[i] = 0.f;
             }
+        }
+        if (a.parts.beta) {
+            for (int idx = tid; idx < cn * K; idx += NT)
+                a.parts.beta[size_t(p0 + i0 + idx / K) * K + idx % K] = s.F[(idx / K) * FLD + idx % K];
         }
         if (!a.predict) {
             __syncthreads();

@@ -47,6 +47,13 @@ struct HeadsSaved {   // per-step state kept in the workspace between forward an
     void *t_b1, *t_b2;   // bf16 operand images of the stacked weight rows (date independent part)
 };
 
+struct HeadsParts {   // stand-alone sub-module calls (fvae_heads_parts): optional inputs / outputs of the per-date heads
+    const float *z_mu, *z_sigma;      // [B][K]  factors handed to the decoder (FactorDecoder.forward's arguments) or NULL
+    float *alpha_mu, *alpha_sigma;    // [S]     AlphaLayer.forward                       module.py:78-84
+    float *beta;                      // [S][K]  BetaLayer.forward                        module.py:92-94
+    float *context;                   // [B][K][H]  AttentionLayer.forward of every head  module.py:134-153
+};
+
 struct HeadsArgs {
     int S, B, H, K, M;
     const int* date_ptr;        // [B+1]
@@ -59,6 +66,7 @@ struct HeadsArgs {
     fvae_outputs out;
     HeadsW w;
     HeadsSaved sv;
+    HeadsParts parts;           // all NULL inside the ELBO step
 };
 
 #ifdef __CUDACC__

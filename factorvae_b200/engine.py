@@ -323,6 +323,82 @@ def latent(st: StepState) -> torch.Tensor:
     return st.workspace[off:off + S * H * 4].view(torch.float32).view(S, H).clone()
 
 
+def heads_parts(layout: ParamLayout, flat: torch.Tensor, e: torch.Tensor, *, y: Optional[torch.Tensor] = None,
+                z: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, train: bool = False,
+                eps: Optional[torch.Tensor] = None, keep_mask: Optional[torch.Tensor] = None,
+                philox: Optional[Tuple[int, int, int]] = None, want=()) -> Dict[str, torch.Tensor]:
+    """The per-date sub-modules on caller-supplied stock latents e (N, H) of ONE date (fvae_heads_parts): FactorEncoder
+    (needs y), FactorPredictor / AttentionLayer, AlphaLayer, BetaLayer, FactorDecoder (z = (mu, sigma) or the prior).
+    `want` names the optional outputs to produce: "alpha", "beta", "context".  Forward only."""
+    L = _cabi.lib()
+    _require_cuda(flat, "parameters")
+    _require_cuda(e, "stock_latent")
+    dev = e.device
+    if flat.device != dev:
+        raise RuntimeError(f"parameters live on {flat.device}, stock_latent on {dev}")
+    if e.dim() != 2 or e.shape[1] != layout.H:
+        raise ValueError(f"stock_latent must be (N, {layout.H}), got {tuple(e.shape)}")
+    e = e.detach().to(torch.float32).contiguous()
+    N, H, K, M = e.shape[0], layout.H, layout.K, layout.M
+    shape = _cabi.Shape(N, 1, 1, layout.C, H, K, M)
+    f32 = dict(dtype=torch.float32, device=dev)
+    keep: Dict[str, torch.Tensor] = dict(e=e)
+    flags = _cabi.FLAG_TRAIN if train else 0
+    if philox is not None:
+        flags |= _cabi.FLAG_PHILOX
+        noise = _cabi.Noise(None, None, int(philox[0]) & (2 ** 64 - 1), int(philox[1]), int(philox[2]))
+    else:
+        if eps is None:
+            raise ValueError("either eps (and keep_mask in train mode) or philox=(seed, step, unit_base) is required")
+        keep["eps"] = eps = eps.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if eps.numel() != N:
+            raise ValueError("eps must have one entry per stock")
+        km_ptr = None
+        if train:
+            if keep_mask is None or tuple(keep_mask.shape) != (N, K):
+                raise ValueError("train mode needs keep_mask (N, K) or philox")
+            keep["keep_mask"] = keep_mask = keep_mask.to(device=dev, dtype=torch.uint8).contiguous()
+            km_ptr = keep_mask.data_ptr()
+        noise = _cabi.Noise(eps.data_ptr(), km_ptr, 0, 0, 0)
+    out = dict(loss=torch.empty(1, **f32), date_loss=torch.empty(1, **f32), yhat=torch.empty(N, **f32), mu_y=torch.empty(N, **f32),
+               sigma_y=torch.empty(N, **f32), mu_post=torch.empty(K, **f32), sigma_post=torch.empty(K, **f32),
+               mu_prior=torch.empty(K, **f32), sigma_prior=torch.empty(K, **f32))
+    outs = _cabi.Outputs(*[out[n].data_ptr() for n, _ in _cabi.Outputs._fields_])
+    parts = _cabi.Parts(None, None, None, None, None, None)
+    if z is not None:
+        keep["z_mu"] = zm = z[0].detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        keep["z_sigma"] = zs = z[1].detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if zm.numel() != K or zs.numel() != K:
+            raise ValueError(f"factor_mu / factor_sigma must have {K} entries")
+        parts.z_mu, parts.z_sigma = zm.data_ptr(), zs.data_ptr()
+    if "alpha" in want:
+        out["alpha_mu"], out["alpha_sigma"] = torch.empty(N, 1, **f32), torch.empty(N, 1, **f32)
+        parts.alpha_mu, parts.alpha_sigma = out["alpha_mu"].data_ptr(), out["alpha_sigma"].data_ptr()
+    if "beta" in want:
+        out["beta"] = torch.empty(N, K, **f32)
+        parts.beta = out["beta"].data_ptr()
+    if "context" in want:
+        out["context"] = torch.empty(K, H, **f32)
+        parts.context = out["context"].data_ptr()
+    y_ptr = None
+    if y is not None:
+        _require_cuda(y, "returns")
+        keep["y"] = y = y.detach().to(dtype=torch.float32).reshape(-1).contiguous()
+        if y.numel() != N:
+            raise ValueError("returns must have one entry per stock")
+        y_ptr = y.data_ptr()
+    need = L.fvae_workspace_bytes(C.byref(shape), _cabi.PREC_FP32)
+    if need < 0:
+        _cabi.check(int(need), "fvae_workspace_bytes")
+    ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+    date_ptr = single_date_ptr(N, dev)
+    with _on(dev):
+        rc = L.fvae_heads_parts(C.byref(shape), e.data_ptr(), y_ptr, date_ptr.data_ptr(), flat.data_ptr(), C.byref(noise), flags,
+                                C.byref(parts), C.byref(outs), ws.data_ptr(), ws.numel(), _stream(dev))
+    _cabi.check(rc, "fvae_heads_parts")
+    return out
+
+
 def fe_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, precision: str = "fp32"):
     L = _cabi.lib()
     _require_cuda(flat, "parameters")

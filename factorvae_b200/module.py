@@ -114,11 +114,38 @@ class FeatureExtractor(nn.Module):
         return _FeFn.apply(self, x, *params)
 
 
-def _standalone(who: str):
-    raise NotImplementedError(
-        f"{who}.forward is not a separate kernel: on this framework the encoder / decoder / predictor heads of a "
-        "date run fused inside FactorVAE.forward and FactorVAE.prediction (the only call sites in the reference's "
-        "main.py / train_model.py / utils.py). Call those; FeatureExtractor.forward is available on its own.")
+_PART_STEP = [0]
+_WARNED = set()
+
+
+def _parts(who: str, named: dict, H: int, K: int, M: int, stock_latent: torch.Tensor, *, train: bool = False, **kw):
+    """One stand-alone sub-module call (include/fvae_b200.h: fvae_heads_parts).  `named` maps reference state_dict names of
+    the full model to this module's parameters; the sections of the other modules stay zero.  Forward only: the outputs
+    carry no autograd edge (the gradient of the heads exists inside FactorVAE.forward's backward)."""
+    import warnings
+    _cuda_only(stock_latent, who + ".forward")
+    if torch.is_grad_enabled() and who not in _WARNED and (stock_latent.requires_grad or any(p.requires_grad for p in named.values())):
+        _WARNED.add(who)
+        warnings.warn(f"{who}.forward on its own is forward-only on factorvae_b200: its outputs are not attached to autograd. "
+                      "Train through FactorVAE.forward (the reference's only call site); use torch.no_grad() to silence this.")
+    layout = engine.ParamLayout(1, H, K, M)
+    flat = torch.zeros(layout.total, dtype=torch.float32, device=stock_latent.device)
+    for name, p in named.items():
+        layout.view(flat, name).copy_(p.detach())
+    N = stock_latent.shape[0]
+    if _INJECTED is not None:
+        eps, km = _INJECTED
+        if eps is None:
+            eps = torch.zeros(N, device=stock_latent.device)
+        kw.update(eps=eps, keep_mask=km if train else None)
+    else:
+        _PART_STEP[0] += 1
+        kw.update(philox=(torch.initial_seed() ^ 0x5DEECE66D, _PART_STEP[0], 0))
+    return engine.heads_parts(layout, flat, stock_latent, train=train, **kw)
+
+
+def _sub(prefix: str, mod: nn.Module) -> dict:
+    return {prefix + n: p for n, p in mod.named_parameters()}
 
 
 class FactorEncoder(nn.Module):
@@ -134,7 +161,12 @@ class FactorEncoder(nn.Module):
         self.softplus = nn.Softplus()
 
     def forward(self, stock_latent, returns):
-        _standalone("FactorEncoder")
+        """(N, H), (N, 1) | (N,) -> (factor_mu (K,), factor_sigma (K,)), reference module.py:52-67.  A sigma that underflows to
+        exactly 0 comes back as 1e-6 (the :117 clamp the decoder would apply is fused into the kernel)."""
+        _cuda_only(returns, "FactorEncoder.forward")
+        o = _parts("FactorEncoder", _sub("factor_encoder.", self), self.linear.in_features, self.linear_mu.out_features,
+                   self.linear.out_features, stock_latent, y=returns)
+        return o["mu_post"], o["sigma_post"]
 
 
 class AlphaLayer(nn.Module):
@@ -149,7 +181,10 @@ class AlphaLayer(nn.Module):
         self.softplus = nn.Softplus()
 
     def forward(self, stock_latent):
-        _standalone("AlphaLayer")
+        """(N, H) -> (alpha_mu (N, 1), alpha_sigma (N, 1)), reference module.py:78-84."""
+        o = _parts("AlphaLayer", _sub("factor_decoder.alpha_layer.", self), self.linear1.in_features, 1, 1, stock_latent,
+                   want=("alpha",))
+        return o["alpha_mu"], o["alpha_sigma"]
 
 
 class BetaLayer(nn.Module):
@@ -160,7 +195,10 @@ class BetaLayer(nn.Module):
         self.linear1 = nn.Linear(hidden_size, num_factors)
 
     def forward(self, stock_latent):
-        _standalone("BetaLayer")
+        """(N, H) -> beta (N, K), reference module.py:92-94."""
+        o = _parts("BetaLayer", _sub("factor_decoder.beta_layer.", self), self.linear1.in_features, self.linear1.out_features, 1,
+                   stock_latent, want=("beta",))
+        return o["beta"]
 
 
 class FactorDecoder(nn.Module):
@@ -171,8 +209,19 @@ class FactorDecoder(nn.Module):
         self.alpha_layer = alpha_layer
         self.beta_layer = beta_layer
 
+    def reparameterize(self, mu, sigma):
+        """mu + eps * sigma (reference module.py:103-105); inside forward the draw happens in the kernel."""
+        return mu + torch.randn_like(sigma) * sigma
+
     def forward(self, stock_latent, factor_mu, factor_sigma):
-        _standalone("FactorDecoder")
+        """(N, H), (K,), (K,) -> sampled returns (N, 1), reference module.py:107-123; zeros of factor_sigma are replaced by
+        1e-6 in the caller's tensor too, as :117 does through its view."""
+        beta = self.beta_layer.linear1
+        with torch.no_grad():
+            factor_sigma.masked_fill_(factor_sigma == 0, 1e-6)
+        o = _parts("FactorDecoder", _sub("factor_decoder.", self), beta.in_features, beta.out_features, 1, stock_latent,
+                   z=(factor_mu, factor_sigma))
+        return o["yhat"].reshape(-1, 1)
 
 
 class AttentionLayer(nn.Module):
@@ -187,7 +236,12 @@ class AttentionLayer(nn.Module):
         self.dropout = nn.Dropout(0.1)
 
     def forward(self, stock_latent):
-        _standalone("AttentionLayer")
+        """(N, H) -> context vector (H,), zeros if the attention weights hold NaN / Inf (reference module.py:134-153).
+        Dropout on the scores follows self.training."""
+        H = self.key_layer.in_features
+        o = _parts("AttentionLayer", _sub("factor_predictor.attention_layers.0.", self), H, 1, 1, stock_latent,
+                   train=self.training, want=("context",))
+        return o["context"].reshape(H)
 
 
 class FactorPredictor(nn.Module):
@@ -204,7 +258,11 @@ class FactorPredictor(nn.Module):
         self.softplus = nn.Softplus()
 
     def forward(self, stock_latent):
-        _standalone("FactorPredictor")
+        """(N, H) -> (pred_mu (K,), pred_sigma (K,)), reference module.py:169-188.  A sigma that underflows to exactly 0 comes
+        back as 1e-6 (the :264-265 clamp of FactorVAE.forward is fused into the kernel)."""
+        o = _parts("FactorPredictor", _sub("factor_predictor.", self), self.hidden_size, self.num_factor, 1, stock_latent,
+                   train=self.training)
+        return o["mu_prior"], o["sigma_prior"]
 
 
 class _ElboFn(torch.autograd.Function):

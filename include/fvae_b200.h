@@ -12,6 +12,8 @@
  *   fvae_predict        <- FactorVAE.prediction         module.py:273-278
  *   fvae_fe_forward     <- FeatureExtractor.forward     module.py:22-31
  *   fvae_fe_backward    <- autograd of FeatureExtractor.forward
+ *   fvae_heads_parts    <- FactorEncoder / AlphaLayer / BetaLayer / FactorDecoder / AttentionLayer / FactorPredictor .forward
+ *                          called on their own   module.py:52-67, :78-84, :92-94, :107-123, :134-153, :169-188
  *   fvae_param_*        <- the nn.Parameter inventory   module.py:17-20,37-41,72-75,90,129-131,163-166
  *
  * Conventions
@@ -36,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FVAE_ABI_VERSION 4
+#define FVAE_ABI_VERSION 5
 
 /* status codes (<0: argument errors) */
 #define FVAE_OK 0
@@ -154,6 +156,32 @@ int fvae_fe_forward(const fvae_shape* shape, const fvae_panel* x, const float* p
                     float* e, void* workspace, int64_t workspace_bytes, void* stream);
 int fvae_fe_backward(const fvae_shape* shape, const fvae_panel* x, const float* params, int32_t precision,
                      const float* de, float* grad, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Stand-alone calls of the per-date sub-modules on caller-supplied stock latents e[S][H] (what FeatureExtractor.forward
+ * returns), replacing the PyTorch arithmetic of
+ *     FactorEncoder.forward      module.py:52-67    -> out->mu_post, out->sigma_post            (needs y)
+ *     FactorPredictor.forward    module.py:169-188  -> out->mu_prior, out->sigma_prior
+ *     AttentionLayer.forward     module.py:134-153  -> parts->context [B][K][H] (zeros where the NaN/Inf guard :149 tripped)
+ *     AlphaLayer.forward         module.py:78-84    -> parts->alpha_mu, parts->alpha_sigma [S]
+ *     BetaLayer.forward          module.py:92-94    -> parts->beta [S][K]
+ *     FactorDecoder.forward      module.py:107-123  -> out->yhat (sample), out->mu_y, out->sigma_y from the factors
+ *                                                      parts->z_mu / z_sigma [B][K] (sigma == 0 -> 1e-6 as :117)
+ * in ONE launch of the fp32 heads kernel per call.  y == NULL: the encoder and the loss are skipped (out->loss, date_loss,
+ * mu_post, sigma_post may be NULL) and, without z_mu, the decoder is fed the prior like FactorVAE.prediction; y != NULL: the
+ * whole per-date forward of FactorVAE.forward runs from e.  FVAE_FLAG_TRAIN is honoured (dropout on the attention scores).
+ * shape->T and shape->C only size the parameter layout and the workspace (fvae_workspace_bytes(shape, FVAE_PREC_FP32)).
+ * Forward only: the gradient of the heads exists inside fvae_elbo_backward. */
+typedef struct fvae_parts {
+    const float* z_mu;      /* [B][K] or NULL */
+    const float* z_sigma;   /* [B][K] or NULL (both or neither) */
+    float* alpha_mu;        /* [S] or NULL */
+    float* alpha_sigma;     /* [S] or NULL (both or neither) */
+    float* beta;            /* [S][K] or NULL */
+    float* context;         /* [B][K][H] or NULL */
+} fvae_parts;
+int fvae_heads_parts(const fvae_shape* shape, const float* latent, const float* y, const int32_t* date_ptr, const float* params,
+                     const fvae_noise* noise, uint32_t flags, const fvae_parts* parts, const fvae_outputs* out, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 
 /* diagnostics: re-launch ONLY the dominant tensor-core kernel (front forward: LayerNorm -> GEMM -> LeakyReLU -> GEMM)
  * on a workspace that a previous fvae_elbo_forward(FVAE_PREC_BF16_TC) call prepared; bench.py times it with CUDA
