@@ -389,6 +389,28 @@ def main():
     ms_per_step = ms / args.steps
     value = S_global / (ms_per_step * 1e-3)
 
+    # ---- launch-bound workloads (the reference's own per-date step, configs[0]): the same step captured in a CUDA graph
+    graph_detail = None
+    if world == 1 and micro >= B and S <= 8192:
+        try:
+            g = stepper.capture(x, y, date_ptr, unit_base=unit_base, train=True)
+            for _ in range(max(3, args.warmup)):
+                g.replay()
+            torch.cuda.synchronize()
+            nrep = max(50, args.steps)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(nrep):
+                g.replay()
+            g1.record()
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1) / nrep
+            graph_detail = {"ms_per_step": gms, "value": S_global / (gms * 1e-3), "replays": nrep, "loss": float(stepper.loss.item()),
+                            "note": "DateShardedStep.capture: forward + backward of this batch shape replayed as ONE CUDA graph launch; "
+                                    "Philox step counter in device memory (fvae_noise.step_dev), advanced by the graph"}
+        except Exception as exc:                        # diagnostics only: never take the bench line down
+            graph_detail = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
     # ---- roofline of the dominant kernel, timed ALONE with CUDA events on the launching stream
     # dominant kernel = the front forward (K1: LayerNorm -> GEMM 128x160x160 -> LeakyReLU -> GEMM 128xNCx160 per item);
     # algorithmic work per launch: FLOPs = S*T*2*(C^2 + 3HC); bytes = one read of the bf16 panel (S*T*C*2).
@@ -596,6 +618,7 @@ def main():
                            "collective": ("one all-reduce of the flat fp32 gradient (+ loss) per step: " +
                                           ("one kernel over NVLink peer memory (fvae_p2p_allreduce)" if stepper.p2p is not None else "ncclAllReduce"))
                                          if world > 1 else "none"},
+                "cuda_graph": graph_detail,
                 "loss": loss_val, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "e2e": e2e}
         print(json.dumps(line), flush=True)

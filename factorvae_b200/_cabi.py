@@ -13,7 +13,7 @@ F32, BF16 = 0, 1
 PREC_FP32, PREC_BF16_TC = 0, 1
 FLAG_TRAIN, FLAG_PHILOX = 1, 2
 FILL_NONE, FILL_FFILL, FILL_FFILL_BFILL = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 SECTIONS = [
     "LN_W", "LN_B", "W1", "B1", "WIH", "WHH", "BIH", "BHH",
@@ -37,7 +37,7 @@ class Panel(C.Structure):
 
 class Noise(C.Structure):
     _fields_ = [("eps", C.c_void_p), ("keep_mask", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
-                ("unit_base", C.c_int64)]
+                ("unit_base", C.c_int64), ("step_dev", C.c_void_p)]
 
 
 class Outputs(C.Structure):

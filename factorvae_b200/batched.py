@@ -65,10 +65,11 @@ class DateShardedStep:
     def loss(self) -> torch.Tensor:
         return self.gradbuf[self.layout.total: self.layout.total + 1]
 
-    def _local(self, x, y, date_ptr, *, unit_base=0, train=True, eps=None, keep_mask=None):
+    def _local(self, x, y, date_ptr, *, unit_base=0, train=True, eps=None, keep_mask=None, step_dev=None):
         """Forward + backward over the given dates into self.gradbuf (gradient of the MEAN over these dates, loss in the
-        tail); no collective."""
-        noise = dict(eps=eps, keep_mask=keep_mask) if eps is not None else dict(philox=(self.seed, self.step_index, unit_base))
+        tail); no collective.  step_dev: a device word that holds the Philox step counter (graph-captured steps)."""
+        step = self.step_index if step_dev is None else step_dev
+        noise = dict(eps=eps, keep_mask=keep_mask) if eps is not None else dict(philox=(self.seed, step, unit_base))
         out, st = engine.elbo_forward(self.layout, self.flat, x, y, date_ptr, train=train, precision=self.precision,
                                       workspace=self.workspace, loss_out=self.loss, out_cache=self._outs, **noise)
         self.workspace = st.workspace
@@ -124,6 +125,10 @@ class DateShardedStep:
                 acc.add_(self.gradbuf, alpha=w)
         self._reduce(acc, 1.0)
         self.gradbuf.copy_(acc)
+
+    def capture(self, x, y: torch.Tensor, date_ptr: torch.Tensor, *, unit_base: int = 0, train: bool = True) -> "GraphedStep":
+        """Capture forward + backward of this batch SHAPE in a CUDA graph (single GPU): see GraphedStep."""
+        return GraphedStep(self, x, y, date_ptr, unit_base=unit_base, train=train)
 
     def step_from_host(self, x_host: torch.Tensor, y_host: torch.Tensor, date_ptr_host: torch.Tensor, **kw):
         """End-to-end entry: pinned HOST buffers in, loss (a Python float) out -- the H2D copy of the
@@ -189,3 +194,46 @@ class DateShardedStep:
         """Expose the flat gradient as `.grad` of the model's parameters (views, no copy)."""
         for name, p in model.named_parameters():
             p.grad = self.layout.view(self.grad, name)
+
+
+class GraphedStep:
+    """One ELBO step (forward + backward into stepper.grad / stepper.loss) of a fixed batch shape, captured once in a CUDA graph
+    and replayed with one launch.  For launch-bound batches -- the reference's own per-date step (BASELINE.json configs[0]:
+    64 stocks, ~15 kernels of a few microseconds each) -- the host-side launch path, not the GPU, sets the step time.
+
+    `x`, `y`, `date_ptr` are the STATIC inputs: refill them in place (`x.copy_(...)`) between replays.  Kernel arguments are frozen
+    at capture, so the Philox step counter lives in device memory (fvae_noise.step_dev) and the graph itself increments it:
+    replay k draws exactly what `DateShardedStep.step` draws at step_index = first_step + k.  Parameters are read through
+    stepper.flat at replay time, so an optimizer stepping them in place between replays is seen.  Single GPU only (the NVLink
+    all-reduce takes its epoch as a kernel argument)."""
+
+    def __init__(self, stepper: DateShardedStep, x, y: torch.Tensor, date_ptr: torch.Tensor, *, unit_base: int = 0,
+                 train: bool = True, warmup: int = 2):
+        if stepper.world != 1:
+            raise NotImplementedError("graph capture of the step covers the single-GPU path")
+        self.stepper, self.x, self.y, self.date_ptr = stepper, x, y, date_ptr
+        dev = stepper.flat.device
+        self.step_dev = torch.full((1,), int(stepper.step_index), dtype=torch.int64, device=dev)
+        self.out = None
+
+        def body():
+            self.step_dev.add_(1)
+            self.out, _ = stepper._local(x, y, date_ptr, unit_base=unit_base, train=train, step_dev=self.step_dev)
+
+        side = torch.cuda.Stream(dev)                     # warm-up off the capture: kernel attributes, workspace, output tensors
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        # the warm-up and the capture pass advanced the counter's initial value by warmup (capture itself does not execute)
+        stepper.step_index = int(self.step_dev.item())
+
+    def replay(self):
+        """Run the captured step; returns the output dict (static tensors, overwritten by the next replay)."""
+        self.graph.replay()
+        self.stepper.step_index += 1
+        return self.out

@@ -162,6 +162,7 @@ __device__ __forceinline__ void merge_state(float& m, float& l, float m2, float 
 template <int HP>
 __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
+    const uint64_t nstep = noise_step(a);
     const int H = a.H, K = a.K, M = a.M;
     const int d = blockIdx.x, tid = threadIdx.x;
     const int p0 = a.date_ptr[d], n = a.date_ptr[d + 1] - p0;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
                 float x = dot_row<HP>(w, er) + bias;
                 if (is_att) {
                     x = x / tau;
-                    x = x * keep_factor(a, p0 + i0 + i, k);
+                    x = x * keep_factor(a, nstep, p0 + i0 + i, k);
                     x = relu_nan(x);
                     if (!is_finite(x)) bad = 1;
                 }
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
         stage_chunk<HP>(a, s, p0, i0, cn);
         if (tid < CH) {
             s.ys[tid] = (!a.predict && tid < cn) ? a.y[p0 + i0 + tid] : 0.f;
-            s.aux0[tid] = (tid < cn) ? eps_of(a, p0 + i0 + tid) : 0.f;
+            s.aux0[tid] = (tid < cn) ? eps_of(a, nstep, p0 + i0 + tid) : 0.f;
         }
         __syncthreads();
         for (int cb = 0; cb < ncolB; cb += cpbB) {
@@ -467,6 +468,7 @@ __device__ __forceinline__ ColRef col_ref(const HeadsArgs& a, int c) {
 // VEC: stop after the per-date vector phase and hand dyp / dp_k / pooled_k.dp_k to the tensor-core sweep (heads_tc.cu)
 template <int HP, int NB, bool WSM, bool VEC = false>
 __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, float* __restrict__ dE) {
+    const uint64_t nstep = noise_step(a);
     extern __shared__ __align__(16) float smem_raw[];
     const int H = a.H, K = a.K, M = a.M;
     const int d = blockIdx.x, tid = threadIdx.x;
@@ -711,7 +713,7 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                 const int u = p0 + i0 + tid;
                 yv = a.y[u];
                 v1 = coefN * (a.out.yhat[u] - yv);
-                v2 = v1 * eps_of(a, u) / (2.f * a.out.sigma_y[u]);
+                v2 = v1 * eps_of(a, nstep, u) / (2.f * a.out.sigma_y[u]);
             }
             ys[tid] = yv; dmy[tid] = v1; dvv[tid] = v2;
         }
@@ -738,7 +740,7 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
                         const float mk = attm[k], lk = attl[k];
                         for (int i = myslice; i < cn; i += mynsl) {
                             float x = (dot_row<HP>(w, Es + i * HP) + cr.bias) / tau;
-                            const float kf = keep_factor(a, p0 + i0 + i, k);
+                            const float kf = keep_factor(a, nstep, p0 + i0 + i, k);
                             x = x * kf;
                             const float r = relu_nan(x);
                             const float aik = expf(r - mk) / lk;

@@ -70,17 +70,22 @@ struct HeadsArgs {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ float keep_factor(const HeadsArgs& a, int unit, int k) {
+// The Philox step counter of this launch: a kernel argument, or -- for steps captured in a CUDA graph, whose arguments are frozen
+// at capture -- a device word the graph itself advances (fvae_noise.step_dev).  Read once at the top of a kernel.
+__device__ __forceinline__ uint64_t noise_step(const HeadsArgs& a) {
+    return a.noise.step_dev ? *reinterpret_cast<const volatile uint64_t*>(a.noise.step_dev) : a.noise.step;
+}
+__device__ __forceinline__ float keep_factor(const HeadsArgs& a, uint64_t step, int unit, int k) {
     // dropout on the attention scores (module.py:144): kept -> 1/0.9, dropped -> 0; eval -> 1
     if (!(a.flags & FVAE_FLAG_TRAIN)) return 1.f;
     bool keep;
     if (a.noise.keep_mask) keep = a.noise.keep_mask[size_t(unit) * a.K + k] != 0;
-    else keep = philox_keep(a.noise.seed, a.noise.step, a.noise.unit_base + unit, k);
+    else keep = philox_keep(a.noise.seed, step, a.noise.unit_base + unit, k);
     return keep ? kKeepScale : 0.f;
 }
-__device__ __forceinline__ float eps_of(const HeadsArgs& a, int unit) {
+__device__ __forceinline__ float eps_of(const HeadsArgs& a, uint64_t step, int unit) {
     if (a.noise.eps) return a.noise.eps[unit];
-    return philox_normal(a.noise.seed, a.noise.step, a.noise.unit_base + unit);
+    return philox_normal(a.noise.seed, step, a.noise.unit_base + unit);
 }
 // relu that propagates NaN like torch (fmaxf would swallow it)
 __device__ __forceinline__ float relu_nan(float s) { return (s > 0.f || s != s) ? s : 0.f; }

@@ -149,6 +149,7 @@ constexpr uint32_t kColDE = 256, kColDW = 320;
 struct TileIt { int d, t, p0, n; };   // date, tile inside the date, first unit of the date, stocks of the date
 
 __global__ void __launch_bounds__(TNT_ALL, 1) heads_tc_sweep_kernel(HeadsArgs a, HeadsG g, float* __restrict__ dE, TcCols tcg) {
+    const uint64_t nstep = noise_step(a);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int H = a.H, K = a.K, M = a.M, NS = tcg.NS;
     const int tid = threadIdx.x, row = tid & 127, part = tid >> 7, warp = tid >> 5, lane = tid & 31;
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(TNT_ALL, 1) heads_tc_sweep_kernel(HeadsArgs a,
                         const float4 a4 = a4v[k];
                         zs[q] = 0.f; za[q] = 0.f;
                         if (valid && a4.w == 0.f) {
-                            const float kf = keep_factor(a, u, k);
+                            const float kf = keep_factor(a, nstep, u, k);
                             const float x = fs[q] * inv_tau * kf;
                             const float aik = expf(relu_nan(x) - a4.x) * a4.y;
                             za[q] = aik;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(TNT_ALL, 1) heads_tc_sweep_kernel(HeadsArgs a,
                 if (valid) {
                     const float coefN = 2.f / (float(cur.n) * float(a.B));
                     v1 = coefN * (a.out.yhat[u] - a.y[u]);
-                    v2 = v1 * eps_of(a, u) / (2.f * a.out.sigma_y[u]);
+                    v2 = v1 * eps_of(a, nstep, u) / (2.f * a.out.sigma_y[u]);
                 }
                 const float2* b2v = bet2 + pb * 32;
                 for (int kc = 0; kc < tcg.Kp / 8; ++kc) {
@@ -556,6 +557,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane,
 }
 
 __global__ void __launch_bounds__(FNT, 2) heads_tc_fwd_kernel(HeadsArgs a, TcCols tcg) {
+    const uint64_t nstep = noise_step(a);
     extern __shared__ __align__(1024) uint8_t smem[];
     const int H = a.H, K = a.K, M = a.M, NS = tcg.NS, Kp = tcg.Kp, Hp8 = tcg.Hp8;
     const int tid = threadIdx.x, row = tid & 127, grp = tid >> 7, warp = tid >> 5, lane = tid & 31;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(FNT, 2) heads_tc_fwd_kernel(HeadsArgs a, TcCol
         };
         // attention score of (my stock, head k) from the accumulator value: relu(dropout(f / tau)); non-finite -> +inf
         auto att_score = [&](float f, int u, int k) {
-            const float x = relu_nan(f * inv_tau * keep_factor(a, u, k));
+            const float x = relu_nan(f * inv_tau * keep_factor(a, nstep, u, k));
             return (fabsf(x) <= FLT_MAX) ? x : INFINITY;
         };
 
@@ -769,7 +771,7 @@ __global__ void __launch_bounds__(FNT, 2) heads_tc_fwd_kernel(HeadsArgs a, TcCol
                             const float asig = softplus(asp);
                             mu += amu;
                             const float sy = sqrtf(var + asig * asig + 1e-6f);
-                            const float ep = eps_of(a, u);
+                            const float ep = eps_of(a, nstep, u);
                             const float yh = fmaf(ep, sy, mu);
                             a.out.yhat[u] = yh; a.out.mu_y[u] = mu; a.out.sigma_y[u] = sy;
                             if (train_path) {

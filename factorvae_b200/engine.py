@@ -183,6 +183,18 @@ def uniform_date_ptr(B: int, N: int, device) -> torch.Tensor:
     return torch.arange(0, (B + 1) * N, N, dtype=torch.int32, device=device)
 
 
+def _philox_noise(philox, dev, keep: Dict) -> "_cabi.Noise":
+    """philox = (seed, step, unit_base).  `step` is a Python int, or a one-element int64 CUDA tensor: the kernels then read the
+    counter from device memory at run time (fvae_noise.step_dev) -- what a step captured in a CUDA graph needs."""
+    seed, step, base = philox
+    if isinstance(step, torch.Tensor):
+        if step.dtype != torch.int64 or step.numel() != 1 or step.device != dev:
+            raise ValueError("a device step counter must be a one-element int64 tensor on the batch's device")
+        keep["step_dev"] = step
+        return _cabi.Noise(None, None, int(seed) & (2 ** 64 - 1), 0, int(base), step.data_ptr())
+    return _cabi.Noise(None, None, int(seed) & (2 ** 64 - 1), int(step), int(base), None)
+
+
 def elbo_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, y: Optional[torch.Tensor],
                  date_ptr: torch.Tensor, *, eps: Optional[torch.Tensor] = None,
                  keep_mask: Optional[torch.Tensor] = None, train: bool = True, precision: str = "fp32",
@@ -216,7 +228,7 @@ def elbo_forward(layout: ParamLayout, flat: torch.Tensor, x: torch.Tensor, y: Op
     keep: Dict[str, torch.Tensor] = dict(x=x, date_ptr=date_ptr, flat=flat)
     if philox is not None:
         flags |= _cabi.FLAG_PHILOX
-        noise = _cabi.Noise(None, None, int(philox[0]) & (2 ** 64 - 1), int(philox[1]), int(philox[2]))
+        noise = _philox_noise(philox, dev, keep)
     else:
         if eps is None:
             raise ValueError("either eps (and keep_mask in train mode) or philox=(seed, step, unit_base) is required")
@@ -346,7 +358,7 @@ def heads_parts(layout: ParamLayout, flat: torch.Tensor, e: torch.Tensor, *, y: 
     flags = _cabi.FLAG_TRAIN if train else 0
     if philox is not None:
         flags |= _cabi.FLAG_PHILOX
-        noise = _cabi.Noise(None, None, int(philox[0]) & (2 ** 64 - 1), int(philox[1]), int(philox[2]))
+        noise = _philox_noise(philox, dev, keep)
     else:
         if eps is None:
             raise ValueError("either eps (and keep_mask in train mode) or philox=(seed, step, unit_base) is required")

@@ -13,6 +13,10 @@ checkpoints load with `load_state_dict`.  At the first forward (and after any `.
 re-homes every parameter as a view of one flat buffer in the library's layout; optimizers keep
 working because they hold the Parameter objects.
 
+The six sub-modules (FactorEncoder, AlphaLayer, BetaLayer, FactorDecoder, AttentionLayer, FactorPredictor) answer when called on
+their own as well -- one launch of the heads kernel on the caller's stock latents (fvae_heads_parts) -- forward only: the reference
+never differentiates them outside FactorVAE.forward, whose backward is the fused one.
+
 Noise: the reference draws eps with `randn_like` (module.py:104, in eval too) and dropout masks
 with `nn.Dropout(0.1)` (module.py:132,144).  Here both come from an in-kernel Philox stream keyed
 by (torch.initial_seed(), step counter, stock, head); `inject_noise` supplies explicit tensors for

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FVAE_ABI_VERSION 5
+#define FVAE_ABI_VERSION 6
 
 /* status codes (<0: argument errors) */
 #define FVAE_OK 0
@@ -95,6 +95,9 @@ typedef struct fvae_noise {
     uint64_t seed;             /* Philox key  (FVAE_FLAG_PHILOX)                                */
     uint64_t step;             /* Philox counter high word: training step                       */
     int64_t unit_base;         /* global index of unit 0 of this call (shard-invariant RNG)     */
+    const uint64_t* step_dev;  /* NULL, or a DEVICE word holding the step counter: it overrides `step` and is read by the
+                                  kernels at run time, so a step captured in a CUDA graph (whose kernel arguments are frozen at
+                                  capture) draws fresh noise on every replay -- the graph itself advances the word        */
 } fvae_noise;
 
 typedef struct fvae_outputs {

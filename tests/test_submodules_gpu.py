@@ -171,15 +171,19 @@ def test_attention_and_predictor_alone(shape, cuda_device):
     hm = F.leaky_relu(ctx_t @ p["linear.weight"].T + p["linear.bias"])
     _close(tmu, (hm @ p["mu_layer.weight"].T + p["mu_layer.bias"]).view(-1))
     _close(tsg, F.softplus(hm @ p["sigma_layer.weight"].T + p["sigma_layer.bias"]).view(-1))
-    # the NaN / Inf guard: one non-finite latent row poisons the softmax -> the head returns zeros (:149-150)
+    # the NaN guard: one NaN latent row (a stock whose features hold NaN) poisons the softmax -> the head returns zeros and the
+    # prior is the bias path of the shared MLP (:149-150)
     bad = e.clone()
-    bad[N // 2, 0] = float("inf")
+    bad[N // 2, 0] = float("nan")
     pred.eval()
     with torch.no_grad():
         z = pred.attention_layers[0](bad.cuda())
-    want = _attention64(p, "attention_layers.0.", bad.double())
-    if not bool(want.abs().sum() > 0):
-        assert torch.count_nonzero(z) == 0
+        gmu, gsg = pred(bad.cuda())
+    assert torch.count_nonzero(_attention64(p, "attention_layers.0.", bad.double())) == 0
+    assert torch.count_nonzero(z) == 0 and z.shape == (H,)
+    hm0 = F.leaky_relu(p["linear.bias"]).expand(K, H)
+    _close(gmu, (hm0 @ p["mu_layer.weight"].T + p["mu_layer.bias"]).view(-1))
+    _close(gsg, F.softplus(hm0 @ p["sigma_layer.weight"].T + p["sigma_layer.bias"]).view(-1))
 
 
 def test_sub_modules_refuse_cpu_inputs_and_warn_about_autograd(cuda_device):
