@@ -277,10 +277,10 @@ __global__ void __launch_bounds__(gru_threads(NB8), (TCOLS == 64 && NB8 <= 3) ? 
                 fence_async_smem();
                 tc_fence_before_sync();
                 __syncthreads();
-                if (tid == 0) {
+                if (warp == 0) {                              // converged issue: one elected lane per UMMA (tc_sm100.cuh: mma_bf16_ss_w)
                     tc_fence_after_sync();
-                    issue_row_gemm(tmem, 0, smem_u32(sH), smem_u32(sWhh), NC, NC, HP / 16);
-                    mma_commit(bar);
+                    issue_row_gemm_w(tmem, 0, smem_u32(sH), smem_u32(sWhh), NC, NC, HP / 16);
+                    mma_commit_w(bar);
                 }
             }
             // a CTA barrier (this step's, or the one that closed the previous tile) separates everybody's reads of
@@ -314,13 +314,11 @@ __global__ void __launch_bounds__(gru_threads(NB8), (TCOLS == 64 && NB8 <= 3) ? 
                 if (t > 0) {
                     if (cblk) {
                         float a8[8], b8[8];
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24), a8);
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 8), b8);
+                        tmem_ld8x2(tmem_addr(tmem, lane_base, blk * 24), tmem_addr(tmem, lane_base, blk * 24 + 8), a8, b8);
                         expand_compact(a8, b8, ghr, ghz, ghn);
                     } else {
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24), ghr);
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 8), ghz);
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 16), ghn);
+                        tmem_ld8x3(tmem_addr(tmem, lane_base, blk * 24), tmem_addr(tmem, lane_base, blk * 24 + 8),
+                                   tmem_addr(tmem, lane_base, blk * 24 + 16), ghr, ghz, ghn);
                     }
                 } else {
 #pragma unroll
@@ -450,17 +448,18 @@ __global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bw
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
-            if (t > 0 && tid == 0) {
+            if (t > 0 && warp == 0) {                         // converged issue (tc_sm100.cuh: mma_bf16_ss_w)
                 tc_fence_after_sync();
-                issue_row_gemm(tmem, 0, smem_u32(sHp), smem_u32(sWhh), NC, NC, HP / 16);
-                mma_commit(&bars[0]);
+                issue_row_gemm_w(tmem, 0, smem_u32(sHp), smem_u32(sWhh), NC, NC, HP / 16);
+                mma_commit_w(&bars[0]);
             }
             unsigned char* gio = reinterpret_cast<unsigned char*>(a.ws.gi) + size_t(st * a.T + t) * NCH * TILE_CH;
-            uint4 hcur[BPT];                     // h_{t-1}, my chunks
-#pragma unroll
-            for (int bb = 0; bb < BPT; ++bb) hcur[bb] = hq[bb];
-            if (t > 1) {                         // next step's h_{t-2}, in flight while the MMA runs
-                const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + t - 2) * HCH * TILE_CH;
+            // (the gate math reads h_{t-1} back from sHp: carrying a second register copy across the prefetch below makes ptxas
+            // rotate registers with moves placed right behind the loads, where the warp then waits out the memory latency)
+            {   // next step's h_{t-2}, in flight while the MMA runs.  Unconditional, with a clamped step (t <= 1 fetches h_0 again; step 0
+                // replaces hq by the constant chunk): a load under `if (t > 1)` lands in temporaries and ptxas puts the predicated
+                // moves into hq right behind it -- the warp then waits out the whole memory latency there (12 % of the stall samples)
+                const unsigned char* hin = reinterpret_cast<const unsigned char*>(a.ws.hall) + size_t(st * a.T + (t > 1 ? t - 2 : 0)) * HCH * TILE_CH;
 #pragma unroll
                 for (int bb = 0; bb < BPT; ++bb) hq[bb] = *reinterpret_cast<const uint4*>(hin + tile_off(TM, row, blk0 + bb));
             }
@@ -477,13 +476,11 @@ __global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bw
                 if (t > 0) {
                     if (cblk) {
                         float a8[8], b8[8];
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24), a8);
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 8), b8);
+                        tmem_ld8x2(tmem_addr(tmem, lane_base, blk * 24), tmem_addr(tmem, lane_base, blk * 24 + 8), a8, b8);
                         expand_compact(a8, b8, ghr, ghz, ghn);
                     } else {
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24), ghr);
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 8), ghz);
-                        tmem_ld8(tmem_addr(tmem, lane_base, blk * 24 + 16), ghn);
+                        tmem_ld8x3(tmem_addr(tmem, lane_base, blk * 24), tmem_addr(tmem, lane_base, blk * 24 + 8),
+                                   tmem_addr(tmem, lane_base, blk * 24 + 16), ghr, ghz, ghn);
                     }
                 } else {
 #pragma unroll
@@ -499,7 +496,7 @@ __global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bw
                     unpack8(gq[3 * bb + 1], giz);
                     unpack8(gq[3 * bb + 2], gin8);
                 }
-                unpack8(hcur[bb], hp);
+                unpack8(*reinterpret_cast<const uint4*>(sHp + tile_off(TM, row, blk)), hp);
                 float dar[8], daz[8], dan[8], dnr[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -537,33 +534,43 @@ __global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bw
                 *reinterpret_cast<uint4*>(sDgh + tile_off(TM, row, 3 * blk + 2)) = pq;
                 }
             }
-            if (t > 0) {
-                const unsigned char* gn = gio - size_t(NCH) * TILE_CH;          // step t-1 of this tile
-#pragma unroll
-                for (int c = 0; c < 3 * BPT; ++c) if (c < nq) gq[c] = *reinterpret_cast<const uint4*>(gn + tile_off(TM, row, 3 * blk0 + c));
-            }
             fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after_sync();
-                issue_row_gemm(tmem, COL_DH, smem_u32(sDgh), smem_u32(sWhhT), HP, HP, NC / 16);       // dh part = dgh . W_hh
-                mma_commit(&bars[1]);
+                issue_row_gemm_w(tmem, COL_DH, smem_u32(sDgh), smem_u32(sWhhT), HP, HP, NC / 16);     // dh part = dgh . W_hh
+                mma_commit_w(&bars[1]);
                 for (int mb = 0; mb < MB; ++mb)                                                          // dW_hh += dgh^T [h_{t-1} | 1]
-                    issue_wgrad(tmem, COL_DW + mb * HP, smem_u32(sDgh), 16 * mb, smem_u32(sHp), HP, dw_started);
-                mma_commit(&bars[2]);
+                    issue_wgrad_acc_w(tmem, COL_DW + mb * HP, smem_u32(sDgh), 16 * mb, smem_u32(sHp), HP, dw_started);
+                mma_commit_w(&bars[2]);
             }
             dw_started = true;
             dw_pending = true;
+            {   // gate pre-activations of step t-1 of this tile, in flight from here until the next gate epilogue.  Issued behind the
+                // proxy fence + barrier (the fence's MEMBAR would wait for them) and unconditional like the h prefetch (step 0
+                // re-reads what it just wrote and drops it)
+                const unsigned char* gn = gio - size_t(t > 0 ? NCH : 0) * TILE_CH;
+#pragma unroll
+                for (int c = 0; c < 3 * BPT; ++c) if (c < nq) gq[c] = *reinterpret_cast<const uint4*>(gn + tile_off(TM, row, 3 * blk0 + c));
+            }
             mbar_wait(&bars[1], ph1);
             ph1 ^= 1;
             tc_fence_after_sync();
+            if constexpr (BPT == 3) {                           // one TMEM round trip for the three blocks of my row
+                float v0[8], v1[8], v2[8];
+                tmem_ld8x3(tmem_addr(tmem, lane_base, COL_DH + blk0 * 8), tmem_addr(tmem, lane_base, COL_DH + blk0 * 8 + 8),
+                           tmem_addr(tmem, lane_base, COL_DH + blk0 * 8 + 16), v0, v1, v2);
 #pragma unroll
-            for (int bb = 0; bb < BPT; ++bb) {
-                float v[8];
-                tmem_ld8(tmem_addr(tmem, lane_base, COL_DH + (blk0 + bb) * 8), v);
+                for (int u = 0; u < 8; ++u) { dh[u] += v0[u]; dh[8 + u] += v1[u]; dh[16 + u] += v2[u]; }
+            } else {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) dh[bb * 8 + u] += v[u];
+                for (int bb = 0; bb < BPT; ++bb) {
+                    float v[8];
+                    tmem_ld8(tmem_addr(tmem, lane_base, COL_DH + (blk0 + bb) * 8), v);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) dh[bb * 8 + u] += v[u];
+                }
             }
             tc_fence_before_sync();
         }

@@ -193,6 +193,36 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// several 8-column reads of my lane behind ONE wait (each tmem_ld8 pays its own TMEM round trip; on a latency-bound chain like the
+// GRU step that is three round trips per gate block instead of one)
+__device__ __forceinline__ void tmem_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, float (&a)[8], float (&b)[8], float (&c)[8]) {
+    uint32_t r[24];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+        : "r"(t0), "r"(t1), "r"(t2)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); c[i] = __uint_as_float(r[16 + i]); }
+}
+__device__ __forceinline__ void tmem_ld8x2(uint32_t t0, uint32_t t1, float (&a)[8], float (&b)[8]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(t0), "r"(t1)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[8 + i]); }
+}
 // hardware tanh (MUFU.TANH), |rel err| ~ 2^-11: used only on the bf16 tensor-core path
 __device__ __forceinline__ float tanh_fast(float x) {
     float y;
@@ -254,6 +284,29 @@ __device__ __forceinline__ void issue_row_gemm_w(uint32_t tmem, uint32_t dcol, u
     for (int ks = 0; ks < k16; ++ks) {
         mma_bf16_ss_w(tmem + dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
         ad += astep; bd += bstep;
+    }
+}
+
+__device__ __forceinline__ void issue_row_gemm_acc_w(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t b_addr, uint32_t brows,
+                                                     uint32_t N, int k16, bool accumulate) {
+    const uint32_t idesc = make_idesc_bf16(kTileRows, N, false, false);
+    uint64_t ad = make_smem_desc(a_addr, kTileChunk, 128);
+    uint64_t bd = make_smem_desc(b_addr, brows * 16, 128);
+    const uint64_t astep = (2 * kTileChunk) >> 4, bstep = (2 * brows * 16) >> 4;
+    for (int ks = 0; ks < k16; ++ks) {
+        mma_bf16_ss_w(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        ad += astep; bd += bstep;
+    }
+}
+__device__ __forceinline__ void issue_wgrad_acc_w(uint32_t tmem, uint32_t dcol, uint32_t a_addr, uint32_t a_chunk0, uint32_t b_addr,
+                                                  uint32_t N, bool accumulate) {
+    const uint32_t idesc = make_idesc_bf16(kTileRows, N, true, true);
+    uint64_t ad = make_smem_desc(a_addr + a_chunk0 * kTileChunk, 128, kTileChunk);
+    uint64_t bd = make_smem_desc(b_addr, 128, kTileChunk);
+#pragma unroll
+    for (int ks = 0; ks < int(kTileRows) / 16; ++ks) {
+        mma_bf16_ss_w(tmem + dcol, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        ad += 256 >> 4; bd += 256 >> 4;
     }
 }
 
