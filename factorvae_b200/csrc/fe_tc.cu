@@ -336,15 +336,19 @@ __global__ void __launch_bounds__(gru_threads(NB8), (TCOLS == 64 && NB8 <= 3) ? 
                 }
                 float hv[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = blk * 8 + u;
-                    const float r = sigmoid_fast(gir[u] + ghr[u]);
-                    const float z = sigmoid_fast(giz[u] + ghz[u]);
-                    const float n = tanh_fast(gin8[u] + r * (ghn[u] + sBhn[j]));
-                    float hn = fmaf(z, h[bb * 8 + u] - n, n);   // (1-z) n + z h
-                    if (j >= H) hn = 0.f;
-                    h[bb * 8 + u] = hn;
-                    hv[u] = (j == H) ? 1.f : hn;                 // the ones column of the operand tile
+                for (int p2 = 0; p2 < 4; ++p2) {                 // two hidden units per packed instruction (tc_sm100.cuh: fma2)
+                    const int u = 2 * p2, j = blk * 8 + u;
+                    const float2 r = sigmoid2(add2(make_float2(gir[u], gir[u + 1]), make_float2(ghr[u], ghr[u + 1])));
+                    const float2 z = sigmoid2(add2(make_float2(giz[u], giz[u + 1]), make_float2(ghz[u], ghz[u + 1])));
+                    const float2 hb = add2(make_float2(ghn[u], ghn[u + 1]), *reinterpret_cast<const float2*>(sBhn + j));
+                    const float2 n = tanh2(fma2(r, hb, make_float2(gin8[u], gin8[u + 1])));
+                    const float2 hp = make_float2(h[bb * 8 + u], h[bb * 8 + u + 1]);
+                    float2 hn = fma2(z, fma2(n, splat2(-1.f), hp), n);   // (1-z) n + z h
+                    if (j >= H) hn.x = 0.f;
+                    if (j + 1 >= H) hn.y = 0.f;
+                    h[bb * 8 + u] = hn.x; h[bb * 8 + u + 1] = hn.y;
+                    hv[u] = (j == H) ? 1.f : hn.x;               // the ones column of the operand tile
+                    hv[u + 1] = (j + 1 == H) ? 1.f : hn.y;
                 }
                 const uint4 pk = make_uint4(pack_bf16(hv[0], hv[1]), pack_bf16(hv[2], hv[3]), pack_bf16(hv[4], hv[5]), pack_bf16(hv[6], hv[7]));
                 *reinterpret_cast<uint4*>(sH + tile_off(TM, row, blk)) = pk;
@@ -499,21 +503,28 @@ __global__ void __launch_bounds__(gru_threads(NB8), gru_min_ctas(NB8)) tc_gru_bw
                 unpack8(*reinterpret_cast<const uint4*>(sHp + tile_off(TM, row, blk)), hp);
                 float dar[8], daz[8], dan[8], dnr[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = blk * 8 + u;
-                    const float r = sigmoid_fast(gir[u] + ghr[u]);
-                    const float z = sigmoid_fast(giz[u] + ghz[u]);
-                    const float hn = ghn[u] + sBhn[j];
-                    const float n = tanh_fast(gin8[u] + r * hn);
-                    const float hprev = (j < H) ? hp[u] : 0.f;
-                    const float d = dh[bb * 8 + u];
-                    const float dn = d * (1.f - z);
-                    const float dz = d * (hprev - n);
-                    dan[u] = dn * (1.f - n * n);
-                    dar[u] = dan[u] * hn * r * (1.f - r);
-                    daz[u] = dz * z * (1.f - z);
-                    dnr[u] = dan[u] * r;
-                    dh[bb * 8 + u] = d * z;
+                for (int p2 = 0; p2 < 4; ++p2) {                 // two hidden units per packed instruction (tc_sm100.cuh: fma2)
+                    const int u = 2 * p2, j = blk * 8 + u;
+                    const float2 one = splat2(1.f), neg = splat2(-1.f);
+                    const float2 r = sigmoid2(add2(make_float2(gir[u], gir[u + 1]), make_float2(ghr[u], ghr[u + 1])));
+                    const float2 z = sigmoid2(add2(make_float2(giz[u], giz[u + 1]), make_float2(ghz[u], ghz[u + 1])));
+                    const float2 hn = add2(make_float2(ghn[u], ghn[u + 1]), *reinterpret_cast<const float2*>(sBhn + j));
+                    const float2 n = tanh2(fma2(r, hn, make_float2(gin8[u], gin8[u + 1])));
+                    const float2 hprev = make_float2(j < H ? hp[u] : 0.f, j + 1 < H ? hp[u + 1] : 0.f);
+                    const float2 d = make_float2(dh[bb * 8 + u], dh[bb * 8 + u + 1]);
+                    const float2 omz = fma2(z, neg, one);                             // 1 - z
+                    const float2 dn = mul2(d, omz);
+                    const float2 dz = mul2(d, fma2(n, neg, hprev));                   // d (h_prev - n)
+                    const float2 da = mul2(dn, fma2(mul2(n, neg), n, one));           // dn (1 - n^2)
+                    const float2 dr = mul2(mul2(da, hn), mul2(r, fma2(r, neg, one))); // da hn r (1 - r)
+                    const float2 dzz = mul2(dz, mul2(z, omz));                        // dz z (1 - z)
+                    const float2 dq = mul2(da, r);
+                    const float2 dhz = mul2(d, z);
+                    dan[u] = da.x; dan[u + 1] = da.y;
+                    dar[u] = dr.x; dar[u + 1] = dr.y;
+                    daz[u] = dzz.x; daz[u + 1] = dzz.y;
+                    dnr[u] = dq.x; dnr[u + 1] = dq.y;
+                    dh[bb * 8 + u] = dhz.x; dh[bb * 8 + u + 1] = dhz.y;
                 }
                 const uint4 pr = make_uint4(pack_bf16(dar[0], dar[1]), pack_bf16(dar[2], dar[3]), pack_bf16(dar[4], dar[5]), pack_bf16(dar[6], dar[7]));
                 const uint4 pz = make_uint4(pack_bf16(daz[0], daz[1]), pack_bf16(daz[2], daz[3]), pack_bf16(daz[4], daz[5]), pack_bf16(daz[6], daz[7]));

@@ -230,6 +230,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2, sm_100): one issue slot of the fma pipe carries two lanes' worth of arithmetic.  The GRU
+// gate epilogues are bound by that pipe (a 3-register FFMA holds it for two cycles per warp), and neighbouring hidden units are
+// independent, so their pointwise math is written on pairs.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 tanh2(float2 x) { return make_float2(tanh_fast(x.x), tanh_fast(x.y)); }
+__device__ __forceinline__ float2 sigmoid2(float2 x) { return fma2(tanh2(mul2(x, splat2(0.5f))), splat2(0.5f), splat2(0.5f)); }
 // 8 bf16 (one 16-byte chunk) <-> 8 floats
 __device__ __forceinline__ void unpack8(const uint4& p, float (&v)[8]) {
     const uint32_t w[4] = {p.x, p.y, p.z, p.w};
