@@ -19,6 +19,9 @@
 //
 // HBM traffic: e (S x H fp32) is read twice forward / three times backward, from L2 in practice.
 #include <float.h>
+#include <stdlib.h>
+
+#include <cooperative_groups.h>
 
 #include "heads.cuh"
 
@@ -159,16 +162,24 @@ __device__ __forceinline__ void merge_state(float& m, float& l, float m2, float 
     m = mm;
 }
 
+// Under-filled grids (fewer dates than SMs: the micro-batches of BASELINE configs[3..4]) launch a thread-block CLUSTER per date,
+// gridDim.y = cluster size CS: CTA `crank` sweeps the 64-stock chunks crank, crank + CS, ... in both passes, the per-column softmax
+// states and the per-date sums are exchanged through distributed shared memory and merged in rank order by every CTA (identical
+// bits everywhere), the small per-date phases run redundantly, rank 0 writes the per-date results.
 template <int HP>
 __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
+    namespace cg = cooperative_groups;
     const uint64_t nstep = noise_step(a);
     const int H = a.H, K = a.K, M = a.M;
     const int d = blockIdx.x, tid = threadIdx.x;
+    const int CS = int(gridDim.y), crank = int(blockIdx.y);
+    const bool lead = crank == 0;
+    cg::cluster_group cluster = cg::this_cluster();
     const int p0 = a.date_ptr[d], n = a.date_ptr[d + 1] - p0;
     const int FLD = (K + H) | 1;
     Smem s = carve(smem_raw, HP, H, K, M, FLD);
-    if (n <= 0) { if (tid == 0 && a.out.date_loss) a.out.date_loss[d] = nanf(""); return; }
+    if (n <= 0) { if (tid == 0 && lead && a.out.date_loss) a.out.date_loss[d] = nanf(""); return; }
     const float tau = sqrtf(float(H) + 1e-6f);          // module.py:142, evaluated in fp32
 
     // ---- pass A: online column softmax over the stocks for encoder (M) and attention (K) columns
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
 #pragma unroll
         for (int h = 0; h < HP; ++h) accp[h] = 0.f;
         int bad = 0;
-        for (int i0 = 0; i0 < n; i0 += CH) {
+        for (int i0 = crank * CH; i0 < n; i0 += CS * CH) {
             const int cn = min(CH, n - i0);
             __syncthreads();
             stage_chunk<HP>(a, s, p0, i0, cn);
@@ -251,37 +262,79 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
         __syncthreads();
         if (act && bad) atomicOr(&s.bad[k], 1);
         __syncthreads();
-        if (act && slice == 0) {
-            if (is_att) {
-                for (int q = 1; q < NS; ++q) {
-                    float sc1, sc2;
-                    const float* o = scrA + (size_t(k) * NS + q) * (HP + 2);
-                    if (o[1] > 0.f || o[1] != o[1]) {          // that slice saw at least one stock
-                        merge_state(m, l, o[0], o[1], sc1, sc2);
+        int bd = 0;
+        if (act && slice == 0 && is_att) {
+            for (int q = 1; q < NS; ++q) {
+                float sc1, sc2;
+                const float* o = scrA + (size_t(k) * NS + q) * (HP + 2);
+                if (o[1] > 0.f || o[1] != o[1]) {          // that slice saw at least one stock
+                    merge_state(m, l, o[0], o[1], sc1, sc2);
 #pragma unroll
-                        for (int h = 0; h < HP; ++h) accp[h] = accp[h] * sc1 + o[2 + h] * sc2;
-                    }
+                    for (int h = 0; h < HP; ++h) accp[h] = accp[h] * sc1 + o[2 + h] * sc2;
                 }
             }
+            bd = s.bad[k];
+        }
+        if (CS > 1) {
+            // cluster exchange of the per-column states: X[column of this batch][HP + 3] = {m, l, accy | guard, accp[HP]}
+            constexpr int XS = HP + 3;
+            __syncthreads();                                   // the slice scratch in F has been read
+            float* X = s.F;
+            if (act && slice == 0) {
+                float* xr = X + size_t(cl) * XS;
+                xr[0] = m; xr[1] = l; xr[2] = is_att ? float(bd) : accy;
+                if (is_att) {
+#pragma unroll
+                    for (int h = 0; h < HP; ++h) xr[3 + h] = accp[h];
+                }
+            }
+            cluster.sync();
+            if (act && slice == 0) {
+                m = -INFINITY; l = 0.f; accy = 0.f; bd = 0;
+#pragma unroll
+                for (int h = 0; h < HP; ++h) accp[h] = 0.f;
+                for (int r = 0; r < CS; ++r) {                 // rank order: every CTA of the cluster gets identical bits
+                    const float* o = cluster.map_shared_rank(X, r) + size_t(cl) * XS;
+                    const float m2 = o[0], l2 = o[1], t2 = o[2];
+                    if (is_att) bd |= (t2 != 0.f);
+                    if (l2 > 0.f || l2 != l2) {
+                        float sc1, sc2;
+                        merge_state(m, l, m2, l2, sc1, sc2);
+                        if (is_att) {
+#pragma unroll
+                            for (int h = 0; h < HP; ++h) accp[h] = accp[h] * sc1 + o[3 + h] * sc2;
+                        } else {
+                            accy = accy * sc1 + t2 * sc2;
+                        }
+                    }
+                }
+                if (is_att) s.bad[k] = bd;
+            }
+            cluster.sync();                                    // nobody reuses F while a peer still reads it
+        }
+        if (act && slice == 0) {
             if (is_att) {
-                const int bd = s.bad[k];
-                a.sv.att_m[size_t(d) * K + k] = m;
-                a.sv.att_l[size_t(d) * K + k] = l;
-                a.sv.bad[size_t(d) * K + k] = bd;
+                if (lead) {
+                    a.sv.att_m[size_t(d) * K + k] = m;
+                    a.sv.att_l[size_t(d) * K + k] = l;
+                    a.sv.bad[size_t(d) * K + k] = bd;
+                }
                 const float inv = 1.f / l;
 #pragma unroll
                 for (int h = 0; h < HP; ++h)
                     if (h < H) {
                         const float pv = accp[h] * inv;
                         s.pooled[k * H + h] = pv;
-                        a.sv.pooled[(size_t(d) * K + k) * H + h] = pv;
+                        if (lead) a.sv.pooled[(size_t(d) * K + k) * H + h] = pv;
                     }
             } else {
-                a.sv.enc_m[size_t(d) * M + c] = m;
-                a.sv.enc_l[size_t(d) * M + c] = l;
                 const float v = accy / l;
                 s.yp[c] = v;
-                a.sv.yp[size_t(d) * M + c] = v;
+                if (lead) {
+                    a.sv.enc_m[size_t(d) * M + c] = m;
+                    a.sv.enc_l[size_t(d) * M + c] = l;
+                    a.sv.yp[size_t(d) * M + c] = v;
+                }
             }
         }
     }
@@ -298,10 +351,12 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
             const int cl = (sg == 0.f);
             if (cl) sg = kSigmaFloor;
             s.muz[k] = mu; s.sgz[k] = sg;
-            a.out.mu_post[size_t(d) * K + k] = mu;
-            a.out.sigma_post[size_t(d) * K + k] = sg;
-            a.sv.pre_sg_post[size_t(d) * K + k] = pre;
-            a.sv.clamp_post[size_t(d) * K + k] = cl;
+            if (lead) {
+                a.out.mu_post[size_t(d) * K + k] = mu;
+                a.out.sigma_post[size_t(d) * K + k] = sg;
+                a.sv.pre_sg_post[size_t(d) * K + k] = pre;
+                a.sv.clamp_post[size_t(d) * K + k] = cl;
+            }
         }
     }
     // ---- prior: ctx_k = Wv_k pooled_k + bv_k (zeros if the guard tripped), shared MLP head
@@ -314,8 +369,10 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
             for (int h = 0; h < H; ++h) v = fmaf(wv[h], s.pooled[k * H + h], v);
         }
         s.ctx[idx] = v;
-        a.sv.ctx[size_t(d) * K * H + idx] = v;
-        if (a.parts.context) a.parts.context[size_t(d) * K * H + idx] = v;
+        if (lead) {
+            a.sv.ctx[size_t(d) * K * H + idx] = v;
+            if (a.parts.context) a.parts.context[size_t(d) * K * H + idx] = v;
+        }
     }
     __syncthreads();
     float* hm = s.F;     // [K][H] scratch (F is not live yet)
@@ -324,7 +381,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
         float v = a.w.bl[j];
         const float* wl = a.w.Wl + size_t(j) * H;
         for (int h = 0; h < H; ++h) v = fmaf(wl[h], s.ctx[k * H + h], v);
-        a.sv.hm_pre[size_t(d) * K * H + idx] = v;
+        if (lead) a.sv.hm_pre[size_t(d) * K * H + idx] = v;
         hm[idx] = lrelu(v);
     }
     __syncthreads();
@@ -335,10 +392,12 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
         const int cl = (sg == 0.f);
         if (cl) sg = kSigmaFloor;                              // module.py:264-265 (and :117 in prediction)
         s.mupr[k] = mu; s.sgpr[k] = sg;
-        a.out.mu_prior[size_t(d) * K + k] = mu;
-        a.out.sigma_prior[size_t(d) * K + k] = sg;
-        a.sv.pre_sg_prior[size_t(d) * K + k] = pre;
-        a.sv.clamp_prior[size_t(d) * K + k] = cl;
+        if (lead) {
+            a.out.mu_prior[size_t(d) * K + k] = mu;
+            a.out.sigma_prior[size_t(d) * K + k] = sg;
+            a.sv.pre_sg_prior[size_t(d) * K + k] = pre;
+            a.sv.clamp_prior[size_t(d) * K + k] = cl;
+        }
         if (a.predict) { s.muz[k] = mu; s.sgz[k] = sg; }
         if (a.parts.z_mu) {                                    // FactorDecoder.forward on its own: the caller's factors, :117 clamp
             const float zs = a.parts.z_sigma[size_t(d) * K + k];
@@ -356,7 +415,7 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     const int cpbB = ncolB < NT ? ncolB : NT;
     const int NSB = NT / cpbB;
     constexpr int PPS = NT / CH;                                   // threads per stock in the finishing step
-    for (int i0 = 0; i0 < n; i0 += CH) {
+    for (int i0 = crank * CH; i0 < n; i0 += CS * CH) {
         const int cn = min(CH, n - i0);
         __syncthreads();
         stage_chunk<HP>(a, s, p0, i0, cn);
@@ -433,12 +492,30 @@ __global__ void __launch_bounds__(NT) heads_fwd_kernel(HeadsArgs a) {
     }
     if (a.predict) return;
     __syncthreads();
-    if (tid < 2 * K) s.F[tid] = 0.f;
+    for (int i = tid; i < 2 * K; i += NT) s.F[i] = 0.f;
     __syncthreads();
     if (tid / K < NT / K) { atomicAdd(&s.F[tid % K], c1a); atomicAdd(&s.F[K + tid % K], c1b); }
     __syncthreads();
-    if (tid < K) { a.sv.c1_mu[size_t(d) * K + tid] = s.F[tid]; a.sv.c1_sg[size_t(d) * K + tid] = s.F[K + tid]; }
-    const float rec = block_sum(rec_part, s.red) / float(n);           // F.mse_loss: mean over stocks
+    float rec = block_sum(rec_part, s.red);
+    if (CS > 1) {                                                       // per-date sums of the cluster, added in rank order by rank 0
+        if (tid == 0) s.F[2 * K] = rec;
+        cluster.sync();
+        if (lead) {
+            float rs = 0.f;
+            for (int r = 0; r < CS; ++r) rs += cluster.map_shared_rank(s.F, r)[2 * K];
+            rec = rs;
+            for (int i = tid; i < 2 * K; i += NT) {
+                float c1 = 0.f;
+                for (int r = 0; r < CS; ++r) c1 += cluster.map_shared_rank(s.F, r)[i];
+                if (i < K) a.sv.c1_mu[size_t(d) * K + i] = c1; else a.sv.c1_sg[size_t(d) * K + i - K] = c1;
+            }
+        }
+        cluster.sync();                                                 // peers keep their shared memory until rank 0 has read it
+        if (!lead) return;
+    } else {
+        for (int k = tid; k < K; k += NT) { a.sv.c1_mu[size_t(d) * K + k] = s.F[k]; a.sv.c1_sg[size_t(d) * K + k] = s.F[K + k]; }
+    }
+    rec /= float(n);                                                    // F.mse_loss: mean over stocks
     float klp = 0.f;
     for (int k = tid; k < K; k += NT) {                                 // module.py:247
         const float m1 = s.muz[k], s1 = s.sgz[k], m2 = s.mupr[k], s2 = s.sgpr[k];
@@ -899,8 +976,11 @@ size_t fwd_smem_bytes(int HP, int H, int K, int M) {
     size_t fl = size_t(CH) * ((K + H) | 1);
     size_t hm = size_t(K) * H;
     size_t mg = size_t(NT) * (HP + 2);                                       // merge scratch of the statistics sweep
+    size_t xs = size_t(M + K < NT ? M + K : NT) * (HP + 3);                  // cluster exchange of the column states
     size_t mx = fl > hm ? fl : hm;
     if (mg > mx) mx = mg;
+    if (xs > mx) mx = xs;
+    if (size_t(2 * K + 1) > mx) mx = size_t(2 * K + 1);
     return (f + mx) * sizeof(float);
 }
 size_t bwd_vec_smem_bytes(int HP, int H, int K, int M) {
@@ -945,10 +1025,31 @@ int heads_forward(const HeadsArgs& a, cudaStream_t stream) {
     const int HP = pick_hp(a.H);
     const size_t smem = fwd_smem_bytes(HP, a.H, a.K, a.M);
     int rc;
+    // fewer dates than SMs: a cluster of CS CTAs per date (power of two, at most 8 = the portable cluster size, at most one CTA
+    // per 64-stock chunk of an average date, at most what fills the SMs once)
+    int nsm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int avg_chunks = (int((int64_t(a.S) + a.B - 1) / a.B) + CH - 1) / CH;
+    int cs = 1;
+    while (cs < 8 && 2 * cs * a.B <= nsm && 2 * cs <= avg_chunks) cs *= 2;
+    if (getenv("FVAE_HEADS_CLUSTER")) { const int v = atoi(getenv("FVAE_HEADS_CLUSTER")); if (v == 1 || v == 2 || v == 4 || v == 8) cs = v; }
 #define FVAE_LAUNCH_FWD(HPV)                                                        \
     do {                                                                            \
         if ((rc = set_smem(heads_fwd_kernel<HPV>, smem)) != 0) return rc;           \
-        heads_fwd_kernel<HPV><<<a.B, NT, smem, stream>>>(a); count_launch();        \
+        if (cs == 1) {                                                              \
+            heads_fwd_kernel<HPV><<<a.B, NT, smem, stream>>>(a);                    \
+        } else {                                                                    \
+            cudaLaunchConfig_t cfg = {};                                            \
+            cfg.gridDim = dim3(a.B, cs); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \
+            cudaLaunchAttribute at[1];                                              \
+            at[0].id = cudaLaunchAttributeClusterDimension;                         \
+            at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = cs; at[0].val.clusterDim.z = 1; \
+            cfg.attrs = at; cfg.numAttrs = 1;                                       \
+            cudaError_t le = cudaLaunchKernelEx(&cfg, heads_fwd_kernel<HPV>, a);    \
+            if (le != cudaSuccess) return int(le);                                  \
+        }                                                                           \
+        count_launch();                                                             \
     } while (0)
     if (HP == 20) FVAE_LAUNCH_FWD(20); else if (HP == 32) FVAE_LAUNCH_FWD(32); else if (HP == 48) FVAE_LAUNCH_FWD(48); else FVAE_LAUNCH_FWD(64);
 #undef FVAE_LAUNCH_FWD

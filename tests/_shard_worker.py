@@ -77,9 +77,12 @@ def main():
         mx = float((g_all.double() - g1).abs().max() / g1.abs().max())
         lrel = abs(loss_all - l1) / abs(l1)
         n0 = sum(counts[d0:d1])
-        same = torch.equal(out["yhat"], o1["yhat"][base:base + n0]) and torch.equal(out["mu_y"], o1["mu_y"][base:base + n0])
+        # same draws (noise keyed by the global unit id), equal to fp32 round-off: the order of the partial sums over a date's
+        # stocks follows the launch geometry, which follows the number of dates in the call
+        same = (torch.allclose(out["yhat"], o1["yhat"][base:base + n0], rtol=1e-5, atol=1e-6) and
+                torch.allclose(out["mu_y"], o1["mu_y"][base:base + n0], rtol=1e-5, atol=1e-6))
         print(f"G={world} {precision}: grad rel-L2 {rel:.3e} max-rel {mx:.3e}; loss {loss_all:.7f} vs {l1:.7f} (rel {lrel:.2e}); "
-              f"per-unit outputs bit-identical: {same}; p2p vs nccl rel-L2 {d_coll:.2e}; p2p result identical on all ranks: "
+              f"per-unit outputs equal to round-off: {same}; p2p vs nccl rel-L2 {d_coll:.2e}; p2p result identical on all ranks: "
               f"{same_everywhere}; p2p active: {st.p2p is not None}", flush=True)
         # fp32 round-off: the weight-gradient sums are float atomics (order free), bf16 mode adds the tensor-core heads' own
         tol = 2e-6 if precision == "fp32" else 1e-5

@@ -1,6 +1,6 @@
 """Date sharding does not change the step: the gradient all-reduced over G shards of a
-global batch equals the G = 1 gradient of the same batch to fp32 round-off, the loss is identical, per-unit outputs are
-bit-identical (the noise is keyed by the GLOBAL unit id).  One GPU: the all-reduce is emulated by summing the shards' buffers;
+global batch equals the G = 1 gradient of the same batch to fp32 round-off, and so do the loss and the per-unit outputs
+(the noise is keyed by the GLOBAL unit id: every shard draws what the single-GPU step draws).  One GPU: the all-reduce is emulated by summing the shards' buffers;
 two or more GPUs: the real NCCL path under torch.distributed.run (tests/_shard_worker.py)."""
 import os
 import socket
@@ -45,13 +45,13 @@ def test_sharded_gradient_equals_single_gpu_gradient_emulated(precision, G, cuda
         o, _ = part.step(torch.cat(xs[d0:d1]), torch.cat(ys[d0:d1]), ptr, global_dates=B, unit_base=int(cs[d0]), train=True)
         total += part.gradbuf.double()                                         # what all-reduce(SUM) would produce
         a, b = int(cs[d0]), int(cs[d1])
-        assert torch.equal(o["yhat"], o1["yhat"][a:b]) and torch.equal(o["mu_y"], o1["mu_y"][a:b])
-        # per-date vectors: bit-identical in fp32 mode; the tensor-core heads distribute whole dates over persistent CTAs, the
-        # order of their fp32 partial sums follows the CTA a date lands on -> last-bit differences
-        if precision == "fp32":
-            assert torch.equal(o["mu_prior"], o1["mu_prior"][d0:d1])
-        else:
-            assert torch.allclose(o["mu_prior"], o1["mu_prior"][d0:d1], rtol=1e-5, atol=1e-6)
+        # the noise is keyed by the global unit id: the draws are the same, the per-unit outputs equal to fp32 round-off.  Not
+        # bit-identical: the order of the fp32 partial sums over a date's stocks follows the launch geometry, which follows the
+        # number of dates in the call (tensor-core heads: which persistent CTA a date lands on; fp32 heads: the size of the
+        # thread-block cluster that sweeps a date when there are fewer dates than SMs)
+        assert torch.allclose(o["yhat"], o1["yhat"][a:b], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(o["mu_y"], o1["mu_y"][a:b], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(o["mu_prior"], o1["mu_prior"][d0:d1], rtol=1e-5, atol=1e-6)
     gG, lG = total[: L.total], float(total[L.total])
     assert abs(lG - l1) <= 1e-6 * abs(l1), (lG, l1)
     assert float((gG - g1).norm() / g1.norm()) <= (2e-6 if precision == "fp32" else 1e-5)
