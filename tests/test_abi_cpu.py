@@ -95,6 +95,13 @@ def test_module_surface_and_no_cpu_fallback(cabi):
         m.prediction(torch.zeros(4, 20, 158))
     with pytest.raises(NotImplementedError):
         fb.FeatureExtractor(158, 20, num_layers=2)
+    # the sub-modules answer on their own (fvae_heads_parts) -- on CUDA only, like everything else
+    e, y = torch.zeros(4, 20), torch.zeros(4, 1)
+    for call in (lambda: m.factor_encoder(e, y), lambda: m.factor_decoder.alpha_layer(e), lambda: m.factor_decoder.beta_layer(e),
+                 lambda: m.factor_predictor(e), lambda: m.factor_predictor.attention_layers[0](e),
+                 lambda: m.factor_decoder(e, torch.zeros(20), torch.ones(20)), lambda: m.feature_extractor(torch.zeros(4, 20, 158))):
+        with pytest.raises(RuntimeError, match="no CPU"):
+            call()
 
 
 def test_oracle_is_not_imported_by_the_product():
@@ -130,6 +137,22 @@ def test_new_entry_points_validate_arguments_without_a_gpu(cabi):
     assert L.fvae_adam_step(C.c_void_p(20), one, one, one, 10, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) == E_SHAPE  # alignment
     assert L.fvae_rank_ic(None, one, one, 3, 100, one, None) == E_NULL
     assert L.fvae_rank_ic(one, one, one, 3, 5000, one, None) == E_LIMIT                                 # > 4096 stocks per date
+
+
+def test_heads_parts_validates_arguments_without_a_gpu(cabi):
+    import ctypes as C
+    L = cabi.lib()
+    shape = cabi.Shape(64, 1, 1, 1, 20, 20, 128)
+    noise = cabi.Noise(None, None, 1, 1, 0, None)
+    outs = cabi.Outputs(*([1] * 9))
+    parts = cabi.Parts(None, None, None, None, None, None)
+    args = lambda **kw: (C.byref(kw.get("shape", shape)), kw.get("latent", 256), None, 256, 256, C.byref(noise), cabi.FLAG_PHILOX,
+                         C.byref(kw.get("parts", parts)), C.byref(kw.get("outs", outs)), kw.get("ws", 256), 1 << 30, None)
+    assert L.fvae_heads_parts(*args(latent=None)) == -1                                   # FVAE_ERR_NULL
+    assert L.fvae_heads_parts(*args(shape=cabi.Shape(64, 1, 1, 1, 65, 20, 128))) == -3    # H > 64: FVAE_ERR_LIMIT
+    assert L.fvae_heads_parts(*args(ws=257)) == -5                                        # workspace not 256-byte aligned
+    assert L.fvae_heads_parts(*args(parts=cabi.Parts(256, None, None, None, None, None))) == -1   # z_mu without z_sigma
+    assert L.fvae_heads_parts(*args(outs=cabi.Outputs(*([None] * 9)))) == -1              # the decoder outputs are required
 
 
 def test_next_row_modules_have_no_cpu_fallback(cabi):
