@@ -159,22 +159,30 @@ __device__ __forceinline__ void issue_gemm1_tma(uint32_t tmem, uint32_t dcol, ui
 
 // row statistics of one staged row (thread = row): sums over exactly C = 158 features
 __device__ __forceinline__ void row_stats(const unsigned char* xs, int row, int C, float& mean, float& rstd) {
-    float s1 = 0.f, s2 = 0.f;
+    // a 32-bit word holds two bf16 features = one fp32 pair (lo << 16, hi & 0xffff0000): sum and sum of squares run on packed
+    // pairs (FADD2 / FFMA2), half the fma-pipe slots of the scalar form
+    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < KCH; ++j) {
         const uint4 p = *reinterpret_cast<const uint4*>(xs + xs_chunk_off(row, j));
-        float v[8];
-        unpack8(p, v);
+        uint32_t w[4] = {p.x, p.y, p.z, p.w};
         if (j == KCH - 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) if (8 * j + e >= C) v[e] = 0.f;
+            for (int i = 0; i < 4; ++i) {
+                if (8 * j + 2 * i >= C) w[i] = 0u;
+                else if (8 * j + 2 * i + 1 >= C) w[i] &= 0xFFFFu;
+            }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+        for (int i = 0; i < 4; ++i) {
+            const float2 v = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+            s1 = add2(s1, v);
+            s2 = fma2(v, v, s2);
+        }
     }
     const float inv_c = 1.f / float(C);
-    mean = s1 * inv_c;
-    rstd = rsqrtf(fmaxf(s2 * inv_c - mean * mean, 0.f) + kLnEps);
+    mean = (s1.x + s1.y) * inv_c;
+    rstd = rsqrtf(fmaxf((s2.x + s2.y) * inv_c - mean * mean, 0.f) + kLnEps);
 }
 
 // ---- K1 (TMA form) --------------------------------------------------------------------------------------------------
@@ -316,7 +324,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tc_front_tma_kernel(const __gri
                 }
                 uint32_t w[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) w[e] = lrelu_pack(v[2 * e] * st2.y, v[2 * e + 1] * st2.y);      // rstd > 0: rstd lrelu(a) = lrelu(rstd a)
+                for (int e = 0; e < 8; ++e) {                      // rstd > 0: rstd lrelu(a) = lrelu(rstd a)
+                    const float2 t = mul2(make_float2(v[2 * e], v[2 * e + 1]), splat2(st2.y));
+                    w[e] = lrelu_pack(t.x, t.y);
+                }
                 // the ones column (u[:, C] = 1: the GI bias rides in column C of the W_ih image), zeros beyond
                 if (c0 + gq * 16 + 16 > C) {                       // warp-uniform: the last 16-column group of the upper half only
 #pragma unroll
@@ -617,7 +628,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 for (int ch = 0; ch < HALF_CH; ++ch) {
                     uint32_t w[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) w[e] = lrelu_pack(v[8 * ch + 2 * e] * st2.y, v[8 * ch + 2 * e + 1] * st2.y);   // rstd lrelu(acc)
+                    for (int e = 0; e < 4; ++e) {                                           // rstd lrelu(acc)
+                        const float2 t = mul2(make_float2(v[8 * ch + 2 * e], v[8 * ch + 2 * e + 1]), splat2(st2.y));
+                        w[e] = lrelu_pack(t.x, t.y);
+                    }
                     if (ch == one_ch) {                                      // u[:, C] = 1 (the bias row of dW_ih), zeros beyond
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
