@@ -600,12 +600,16 @@ __global__ void __launch_bounds__(TB_THREADS, 1) tc_back_tma_kernel(const __grid
                 ld40(v);
                 const uint32_t mlo = uint32_t(mbits), mhi = uint32_t(mbits >> 32);
                 const float s_pos = st2.y, s_neg = kLeakySlope * st2.y;
+                uint32_t wv[20];
 #pragma unroll
-                for (int e = 0; e < 40; ++e) v[e] *= ((e < 32 ? mlo >> e : mhi >> (e - 32)) & 1u) ? s_pos : s_neg;
+                for (int e = 0; e < 20; ++e) {                     // per pair: two selects of the slope, ONE packed multiply, one pack
+                    const float2 sc = make_float2((((2 * e < 32 ? mlo >> (2 * e) : mhi >> (2 * e - 32)) & 1u) ? s_pos : s_neg),
+                                                  (((2 * e + 1 < 32 ? mlo >> (2 * e + 1) : mhi >> (2 * e + 1 - 32)) & 1u) ? s_pos : s_neg));
+                    const float2 t = mul2(make_float2(v[2 * e], v[2 * e + 1]), sc);
+                    wv[e] = pack_bf16(t.x, t.y);
+                }
 #pragma unroll
-                for (int ch = 0; ch < HALF_CH; ++ch)
-                    pk[ch] = make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
-                                        pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
+                for (int ch = 0; ch < HALF_CH; ++ch) pk[ch] = make_uint4(wv[4 * ch], wv[4 * ch + 1], wv[4 * ch + 2], wv[4 * ch + 3]);
                 tc_fence_before_sync();
                 TL(9);
                 if (k > 0) mbar_wait_relaxed(&dw_done[(k - 1) & 1], uint32_t((k - 1) >> 1) & 1u, 29);      // dW(k-1) has read the u tile

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(TNT_ALL, 1) heads_tc_sweep_kernel(HeadsArgs a,
                         if (valid && a4.w == 0.f) {
                             const float kf = keep_factor(a, nstep, u, k);
                             const float x = fs[q] * inv_tau * kf;
-                            const float aik = expf(relu_nan(x) - a4.x) * a4.y;
+                            const float aik = ex2_fast((relu_nan(x) - a4.x) * kL2E) * a4.y;     // same form as the forward (ex2.approx: 2 ulp)
                             za[q] = aik;
                             zs[q] = (x > 0.f) ? kf * inv_tau * aik * (fa[q] - a4.z) : 0.f;
                         }
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(FNT, 2) heads_tc_fwd_kernel(HeadsArgs a, TcCol
                             for (int q = 0; q < 8; ++q) {
                                 const int k = kc * 8 + q;
                                 float pv = 0.f;
-                                if (kc < Kp / 8 && valid && k < K && !bad[k]) pv = expf(att_score(f[q], u, k) - __int_as_float(attm[k]));
+                                if (kc < Kp / 8 && valid && k < K && !bad[k]) pv = ex2_fast((att_score(f[q], u, k) - __int_as_float(attm[k])) * kL2E);
                                 pz[q] = pv; r[k] = pv;
                             }
                             if (kc < Kp / 8) store8(Pt + tile_off(128, row, kc), pz);
