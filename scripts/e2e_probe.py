@@ -106,3 +106,37 @@ for name, kw in (("bench loop, no upload, deferred read", dict(do_upload=False))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); run_resident(n, **kw); e1.record(); torch.cuda.synchronize()
         print(f"{name:44s} n={n:3d}  {e0.elapsed_time(e1) / n:7.3f} ms/step")
+
+# ---- the date-id H2D of the bench's resident loop: on the compute stream vs prefetched on the copy stream
+dates_h = torch.arange(B, dtype=torch.int32).pin_memory()
+dates_d = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)]
+ids_up = [torch.cuda.Event(), torch.cuda.Event()]
+def run_ids(nsteps, mode):
+    if mode == "copy_stream":
+        with torch.cuda.stream(copy_stream):
+            dates_d[0].copy_(dates_h, non_blocking=True); ids_up[0].record(copy_stream)
+    for i in range(nsteps):
+        b = i & 1
+        if mode == "compute":
+            dates_d[0].copy_(dates_h, non_blocking=True)
+        elif mode == "copy_stream":
+            if i + 1 < nsteps:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done[b ^ 1])      # the step that used this id buffer has finished
+                    dates_d[b ^ 1].copy_(dates_h, non_blocking=True); ids_up[b ^ 1].record(copy_stream)
+            compute.wait_event(ids_up[b])
+        a, bb, c = tables[0].batch(range(B), T)
+        st.step(a, bb, c, train=True)
+        loss_hh[b].copy_(st.loss.reshape(1), non_blocking=True)
+        done[b].record(compute)
+        if i >= 1:
+            done[b ^ 1].synchronize()
+    done[(nsteps - 1) & 1].synchronize()
+for mode in ("none", "compute", "copy_stream"):
+    done[0].record(compute); done[1].record(compute)
+    run_ids(8, mode)
+    torch.cuda.synchronize()
+    for n in (20, 40):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run_ids(n, mode); e1.record(); torch.cuda.synchronize()
+        print(f"resident loop, date ids H2D: {mode:12s} n={n:3d}  {e0.elapsed_time(e1) / n:7.3f} ms/step")
