@@ -680,11 +680,15 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
         sbs = block_sum(sbs, red);
         if (tid == 0 && lead) { atomicAdd(g.bpm, sbm); atomicAdd(g.bps, sbs); }
     }
+    // hm_pre and ctx of the date through shared memory: read from global inside the k loops below they were K dependent L2 round
+    // trips per thread (37 % of this phase's stall samples)
+    for (int idx = tid; idx < K * H; idx += NT) { tmpKH[idx] = a.sv.hm_pre[size_t(d) * K * H + idx]; dps[idx] = a.sv.ctx[size_t(d) * K * H + idx]; }
+    __syncthreads();
     for (int j = tid; j < H; j += NT) {
         float a1 = 0.f, a2 = 0.f, a3 = 0.f;
         const float wm = a.w.wpm[j], ws = a.w.wps[j];
         for (int k = 0; k < K; ++k) {
-            const float pre = a.sv.hm_pre[(size_t(d) * K + k) * H + j];
+            const float pre = tmpKH[k * H + j];
             const float hmv = lrelu(pre);
             a1 = fmaf(dmuprior[k], hmv, a1);
             a2 = fmaf(dpreprior[k], hmv, a2);
@@ -698,9 +702,10 @@ __global__ void __launch_bounds__(NT) heads_bwd_kernel(HeadsArgs a, HeadsG g, fl
     for (int idx = tid; lead && idx < H * H; idx += NT) {  // dWl[j][h] = sum_k dhm_pre[k][j] ctx[k][h]
         const int j = idx / H, h = idx % H;
         float v = 0.f;
-        for (int k = 0; k < K; ++k) v = fmaf(tmpKH[k * H + j], a.sv.ctx[(size_t(d) * K + k) * H + h], v);
+        for (int k = 0; k < K; ++k) v = fmaf(tmpKH[k * H + j], dps[k * H + h], v);
         atomicAdd(g.Wl + idx, v);
     }
+    __syncthreads();                                       // dps (ctx) has been read: it becomes scratch below
     // d ctx[k][h] = sum_j Wl[j][h] dhm_pre[k][j]   (zero behind a tripped guard) -> dps as scratch
     for (int idx = tid; idx < K * H; idx += NT) {
         const int k = idx / H, h = idx % H;
