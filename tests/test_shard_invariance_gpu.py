@@ -58,6 +58,43 @@ def test_sharded_gradient_equals_single_gpu_gradient_emulated(precision, G, cuda
     assert float((gG - g1).abs().max() / g1.abs().max()) <= 2e-5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_micro_batch_accumulation_equals_the_whole_batch_step(precision, cuda_device):
+    """DateShardedStep.step_accumulate (a per-GPU share too large for one workspace: BASELINE configs[3..4]) over unequal
+    micro-batches == step() over the concatenated dates: same draws (global unit ids), gradient and loss to fp32 round-off."""
+    from factorvae_b200 import engine
+    from factorvae_b200.batched import DateShardedStep
+    import factorvae_b200 as fb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _shard_worker import make_batch
+    dev = cuda_device
+    H = K = 20
+    T = 6
+    counts = [300, 257, 128, 301, 64, 299, 300]
+    B = len(counts)
+    torch.manual_seed(42)
+    m = fb.FactorVAE(fb.FeatureExtractor(158, H), fb.FactorEncoder(K, 128, H), fb.FactorDecoder(fb.AlphaLayer(H), fb.BetaLayer(H, K)),
+                     fb.FactorPredictor(H, K))
+    L = engine.ParamLayout(158, H, K, 128)
+    flat = L.pack(m.state_dict(), dev)
+    xs, ys = make_batch(dev, counts, T)
+    cs = torch.tensor([0] + counts).cumsum(0)
+    whole = DateShardedStep(L, flat, precision=precision, seed=11)
+    whole.step(torch.cat(xs), torch.cat(ys), cs.to(torch.int32).to(dev), global_dates=B, unit_base=0, train=True)
+    g1, l1 = whole.grad.double().clone(), float(whole.loss.item())
+    mbs = []
+    for d0, d1 in ((0, 3), (3, 4), (4, 7)):                                   # 3 + 1 + 3 dates
+        ptr = (cs[d0:d1 + 1] - cs[d0]).to(torch.int32).to(dev)
+        mbs.append((torch.cat(xs[d0:d1]), torch.cat(ys[d0:d1]), ptr, int(cs[d0])))
+    acc = DateShardedStep(L, flat, precision=precision, seed=11)
+    acc.step_accumulate(mbs, global_dates=B, train=True)
+    g2, l2 = acc.grad.double(), float(acc.loss.item())
+    assert whole.step_index == acc.step_index == 1
+    assert abs(l2 - l1) <= 1e-6 * abs(l1), (l2, l1)
+    assert float((g2 - g1).norm() / g1.norm()) <= (2e-6 if precision == "fp32" else 1e-5)
+    assert float((g2 - g1).abs().max() / g1.abs().max()) <= 2e-5
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
