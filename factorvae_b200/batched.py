@@ -109,7 +109,9 @@ class DateShardedStep:
         """One step over this rank's dates processed as several micro-batches (a per-GPU share too large for one workspace:
         BASELINE.json configs[3..4] on few GPUs).  micro_batches: iterable of (x, y, date_ptr, unit_base).  Gradients are
         accumulated locally with weight B_micro / B_global, then exchanged ONCE.  The result equals step() over the
-        concatenated dates (noise is keyed by the global unit id)."""
+        concatenated dates (noise is keyed by the global unit id): to fp32 round-off in fp32 mode (measured 1e-7), to the bf16
+        noise of the mode in bf16 mode (measured 1.4e-4 rel-L2: the 1 / B of the call sits inside the bf16 gradient tiles the
+        backward kernels hand to each other) -- tests/test_shard_invariance_gpu.py."""
         self.step_index += 1
         acc = getattr(self, "_acc", None)
         if acc is None:
